@@ -1,0 +1,588 @@
+// api.cu -- the C ABI of include/etgpu.h: contexts, resident data, forests.
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "internal.h"
+
+static thread_local std::string g_last_error;
+
+void et_set_error(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+#define ET_API_BEGIN try {
+#define ET_API_END                                           \
+  }                                                          \
+  catch (const EtError &e) { return e.code; }                \
+  catch (const std::bad_alloc &) {                           \
+    et_set_error("host allocation failed");                  \
+    return ET_ENOMEM;                                        \
+  }                                                          \
+  return ET_OK;
+
+extern "C" int32_t et_abi_version(void) { return ET_ABI_VERSION; }
+extern "C" const char *et_last_error(void) { return g_last_error.c_str(); }
+extern "C" double et_debug_repeat_add(double c, int64_t h) { return et_repeat_add(c, h); }
+
+// ---- context --------------------------------------------------------------------------------
+extern "C" int et_init(int32_t device, et_ctx **out) {
+  ET_API_BEGIN
+  if (!out) ET_FAIL(ET_EINVAL, "et_init: out is NULL");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    ET_FAIL(ET_ECUDA, "et_init: no CUDA device (%s); libetgpu has no CPU fallback",
+            e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= count) ET_FAIL(ET_EINVAL, "et_init: device %d out of range [0,%d)", device, count);
+  CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    ET_FAIL(ET_ECUDA, "et_init: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+            prop.minor);
+  et_ctx *c = new et_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  *out = c;
+  ET_API_END
+}
+
+extern "C" void et_shutdown(et_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+extern "C" int et_set_stream(et_ctx *ctx, void *cuda_stream) {
+  ET_API_BEGIN
+  if (!ctx) ET_FAIL(ET_EINVAL, "et_set_stream: ctx is NULL");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  ET_API_END
+}
+
+extern "C" int et_synchronize(et_ctx *ctx) {
+  ET_API_BEGIN
+  if (!ctx) ET_FAIL(ET_EINVAL, "et_synchronize: ctx is NULL");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ET_API_END
+}
+
+// ---- row-major -> column-major transpose ----------------------------------------------------
+// 32x32 tiles through padded shared memory: coalesced 256-byte row reads, coalesced column writes.
+__global__ void k_transpose(const double *__restrict__ src, int64_t rows, int32_t d, double *__restrict__ dst,
+                            int64_t ld, int64_t row0) {
+  __shared__ double tile[32][33];
+  int64_t r0 = (int64_t)blockIdx.x * 32;
+  int32_t c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int64_t r = r0 + j;
+    int32_t c = c0 + threadIdx.x;
+    if (r < rows && c < d) tile[j][threadIdx.x] = src[r * d + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int32_t c = c0 + j;
+    int64_t r = r0 + threadIdx.x;
+    if (r < rows && c < d) dst[(int64_t)c * ld + row0 + r] = tile[threadIdx.x][j];
+  }
+}
+
+void et_launch_transpose(et_ctx *ctx, const double *src, int64_t rows, int32_t d, double *dst, int64_t ld,
+                         int64_t row0) {
+  if (rows <= 0 || d <= 0) return;
+  dim3 block(32, 8);
+  dim3 grid((unsigned)ceil_div(rows, 32), (unsigned)ceil_div(d, 32));
+  k_transpose<<<grid, block, 0, ctx->stream>>>(src, rows, d, dst, ld, row0);
+  ctx->launches++;
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// ---- data -----------------------------------------------------------------------------------
+static et_data *data_alloc(et_ctx *ctx, int64_t n, int32_t d) {
+  if (n < 0 || d < 0) ET_FAIL(ET_EINVAL, "negative table dimensions");
+  if (n > 0x7fffffff) ET_FAIL(ET_EUNSUPPORTED, "tables with more than 2^31-1 rows are not supported");
+  et_data *D = new et_data();
+  D->ctx = ctx;
+  D->n = n;
+  D->d = d;
+  D->ld = ((n + 15) / 16) * 16;
+  size_t bytes = (size_t)std::max<int64_t>(D->ld, 16) * (size_t)std::max(d, 1) * sizeof(double);
+  cudaError_t e = cudaMalloc((void **)&D->x, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    delete D;
+    ET_FAIL(ET_ENOMEM, "cannot allocate %zu bytes of HBM for the %lld x %d table", bytes, (long long)n, d);
+  }
+  return D;
+}
+
+extern "C" int et_data_dense_alloc(et_ctx *ctx, int64_t n, int32_t d, et_data **out) {
+  ET_API_BEGIN
+  if (!ctx || !out) ET_FAIL(ET_EINVAL, "et_data_dense_alloc: NULL argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  *out = data_alloc(ctx, n, d);
+  ET_API_END
+}
+
+extern "C" int et_data_dense_colblock(et_ctx *ctx, et_data *D, const double *cols, int32_t first_col,
+                                      int32_t n_cols) {
+  ET_API_BEGIN
+  if (!ctx || !D || (!cols && n_cols > 0)) ET_FAIL(ET_EINVAL, "et_data_dense_colblock: NULL argument");
+  if (first_col < 0 || n_cols < 0 || first_col + n_cols > D->d)
+    ET_FAIL(ET_EINVAL, "et_data_dense_colblock: columns [%d,%d) outside [0,%d)", first_col, first_col + n_cols, D->d);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (n_cols > 0 && D->n > 0)
+    CUDA_CHECK(cudaMemcpy2DAsync(D->x + (int64_t)first_col * D->ld, (size_t)D->ld * sizeof(double), cols,
+                                 (size_t)D->n * sizeof(double), (size_t)D->n * sizeof(double), (size_t)n_cols,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ET_API_END
+}
+
+extern "C" int et_data_dense_rowmajor(et_ctx *ctx, const double *x, int64_t n, int32_t d, et_data **out) {
+  ET_API_BEGIN
+  if (!ctx || !out || (!x && n > 0 && d > 0)) ET_FAIL(ET_EINVAL, "et_data_dense_rowmajor: NULL argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  et_data *D = data_alloc(ctx, n, d);
+  if (n > 0 && d > 0) {
+    // staged in row chunks of <= 256 MB so the temporary stays small next to the table
+    int64_t chunk = std::max<int64_t>(1, ((int64_t)256 << 20) / ((int64_t)d * 8));
+    chunk = std::min(chunk, n);
+    double *stage = nullptr;
+    cudaError_t e = cudaMalloc((void **)&stage, (size_t)chunk * d * sizeof(double));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      et_data_free(D);
+      ET_FAIL(ET_ENOMEM, "cannot allocate the upload staging buffer");
+    }
+    try {
+      for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+        int64_t rows = std::min(chunk, n - r0);
+        CUDA_CHECK(cudaMemcpyAsync(stage, x + r0 * d, (size_t)rows * d * sizeof(double), cudaMemcpyHostToDevice,
+                                   ctx->stream));
+        et_launch_transpose(ctx, stage, rows, d, D->x, D->ld, r0);
+      }
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    } catch (...) {
+      cudaFree(stage);
+      et_data_free(D);
+      throw;
+    }
+    cudaFree(stage);
+  }
+  *out = D;
+  ET_API_END
+}
+
+extern "C" int et_data_dense_rowmajor_device(et_ctx *ctx, const double *x_dev, int64_t n, int32_t d,
+                                             et_data **out) {
+  ET_API_BEGIN
+  if (!ctx || !out || (!x_dev && n > 0 && d > 0)) ET_FAIL(ET_EINVAL, "et_data_dense_rowmajor_device: NULL argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  et_data *D = data_alloc(ctx, n, d);
+  try {
+    et_launch_transpose(ctx, x_dev, n, d, D->x, D->ld, 0);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  } catch (...) {
+    et_data_free(D);
+    throw;
+  }
+  *out = D;
+  ET_API_END
+}
+
+template <typename T>
+static void upload_vec(et_ctx *ctx, T **dst, const T *src, int64_t n) {
+  if (*dst) {
+    cudaFree(*dst);
+    *dst = nullptr;
+  }
+  cudaError_t e = cudaMalloc((void **)dst, (size_t)std::max<int64_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *dst = nullptr;
+    ET_FAIL(ET_ENOMEM, "cannot allocate target/weight vector");
+  }
+  if (n > 0) {
+    CUDA_CHECK(cudaMemcpyAsync(*dst, src, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+}
+
+extern "C" int et_data_set_target_classification(et_ctx *ctx, et_data *D, const int32_t *y, int64_t n_target,
+                                                 int32_t num_classes) {
+  ET_API_BEGIN
+  if (!ctx || !D || (!y && n_target > 0)) ET_FAIL(ET_EINVAL, "et_data_set_target_classification: NULL argument");
+  if (n_target != D->n)
+    ET_FAIL(ET_EINVAL, "requirement failed: Data.numRows(%lld) != target.length (%lld)", (long long)D->n,
+            (long long)n_target);
+  if (num_classes <= 0) ET_FAIL(ET_EINVAL, "numClasses must be positive");
+  std::vector<int64_t> hist((size_t)num_classes, 0);
+  for (int64_t i = 0; i < n_target; i++) {
+    if (y[i] < 0 || y[i] >= num_classes)
+      ET_FAIL(ET_EINVAL, "target[%lld] = %d outside [0, numClasses=%d) (ArrayIndexOutOfBounds in the reference)",
+              (long long)i, y[i], num_classes);
+    hist[(size_t)y[i]]++;
+  }
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  upload_vec(ctx, &D->y_cls, y, n_target);
+  D->num_classes = num_classes;
+  D->root_hist = hist;
+  ET_API_END
+}
+
+extern "C" int et_data_set_target_regression(et_ctx *ctx, et_data *D, const double *y, int64_t n_target) {
+  ET_API_BEGIN
+  if (!ctx || !D || (!y && n_target > 0)) ET_FAIL(ET_EINVAL, "et_data_set_target_regression: NULL argument");
+  if (n_target != D->n)
+    ET_FAIL(ET_EINVAL, "requirement failed: Data.numRows(%lld) != target.length (%lld)", (long long)D->n,
+            (long long)n_target);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  upload_vec(ctx, &D->y_reg, y, n_target);
+  ET_API_END
+}
+
+extern "C" int et_data_set_weights(et_ctx *ctx, et_data *D, const double *w, int64_t n_weights) {
+  ET_API_BEGIN
+  if (!ctx || !D) ET_FAIL(ET_EINVAL, "et_data_set_weights: NULL argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (!w) {
+    if (D->w) cudaFree(D->w);
+    D->w = nullptr;
+  } else {
+    if (n_weights != D->n)
+      ET_FAIL(ET_EINVAL, "sampleWeights.length (%lld) != Data.numRows (%lld)", (long long)n_weights, (long long)D->n);
+    for (int64_t i = 0; i < n_weights; i++)
+      if (w[i] < 0.0) ET_FAIL(ET_EINVAL, "requirement failed: Negative weights not allowed.");
+    upload_vec(ctx, &D->w, w, n_weights);
+  }
+  ET_API_END
+}
+
+extern "C" int et_data_dims(const et_data *D, int64_t *n, int32_t *d) {
+  if (!D) {
+    et_set_error("et_data_dims: NULL data");
+    return ET_EINVAL;
+  }
+  if (n) *n = D->n;
+  if (d) *d = D->d;
+  return ET_OK;
+}
+
+extern "C" void et_data_free(et_data *D) {
+  if (!D) return;
+  if (D->ctx) cudaSetDevice(D->ctx->device);
+  if (D->x) cudaFree(D->x);
+  if (D->y_cls) cudaFree(D->y_cls);
+  if (D->y_reg) cudaFree(D->y_reg);
+  if (D->w) cudaFree(D->w);
+  delete D;
+}
+
+// ---- build ----------------------------------------------------------------------------------
+static void check_build_common(et_ctx *ctx, et_data *D, int32_t k, int32_t m, int32_t best_split, et_forest **out) {
+  if (!ctx || !D || !out) ET_FAIL(ET_EINVAL, "build: NULL argument");
+  if (D->ctx != ctx) ET_FAIL(ET_EINVAL, "build: data belongs to another context");
+  if (m < 0) ET_FAIL(ET_EINVAL, "build: m must be >= 0");
+  if (best_split) ET_FAIL(ET_EUNSUPPORTED, "bestSplit=true (pkg:56-202, 298-426) is not implemented on the GPU yet");
+  (void)k;
+}
+
+extern "C" int et_build_classification(et_ctx *ctx, et_data *D, const int32_t *target, int64_t n_target,
+                                       const double *weights, int32_t num_classes, int32_t n_min, int32_t k,
+                                       int32_t m, int32_t parallelism, int32_t best_split, int32_t max_depth,
+                                       int64_t seed, const int32_t *tree_ids, const et_replay *replay,
+                                       et_forest **out, et_stats *stats) {
+  ET_API_BEGIN
+  check_build_common(ctx, D, k, m, best_split, out);
+  if (target) {
+    int rc = et_data_set_target_classification(ctx, D, target, n_target, num_classes);
+    if (rc != ET_OK) return rc;
+    rc = et_data_set_weights(ctx, D, weights, weights ? n_target : 0);
+    if (rc != ET_OK) return rc;
+  }
+  if (!D->y_cls) ET_FAIL(ET_EINVAL, "build: no classification target attached");
+  if (D->num_classes != num_classes) ET_FAIL(ET_EINVAL, "build: numClasses differs from the attached target's");
+  if (D->n == 0 && m > 0) ET_FAIL(ET_EINVAL, "build: empty table (the reference fails on targetInSubset.raw(0))");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  BuildArgs a;
+  a.task = D->w ? 1 : 0;
+  a.num_classes = num_classes;
+  a.n_min = n_min;
+  a.k = k;
+  a.m = m;
+  a.parallelism = parallelism;
+  a.best_split = best_split;
+  a.max_depth = max_depth;
+  a.seed = seed;
+  a.tree_ids = tree_ids;
+  a.replay = replay;
+  et_forest *f = new et_forest();
+  f->ctx = ctx;
+  f->leaf_width = num_classes;
+  f->is_regression = 0;
+  try {
+    et_build_forest(ctx, D, a, f, stats);
+  } catch (...) {
+    delete f;
+    throw;
+  }
+  *out = f;
+  ET_API_END
+}
+
+extern "C" int et_build_regression(et_ctx *ctx, et_data *D, const double *target, int64_t n_target, int32_t n_min,
+                                   int32_t k, int32_t m, int32_t parallelism, int32_t best_split,
+                                   int32_t max_depth, int64_t seed, const int32_t *tree_ids,
+                                   const et_replay *replay, et_forest **out, et_stats *stats) {
+  ET_API_BEGIN
+  check_build_common(ctx, D, k, m, best_split, out);
+  if (target) {
+    int rc = et_data_set_target_regression(ctx, D, target, n_target);
+    if (rc != ET_OK) return rc;
+  }
+  if (!D->y_reg) ET_FAIL(ET_EINVAL, "build: no regression target attached");
+  if (D->n == 0 && m > 0) ET_FAIL(ET_EINVAL, "requirement failed (subset.length > 0, pkg:779)");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  BuildArgs a;
+  a.task = 2;
+  a.num_classes = 1;
+  a.n_min = n_min;
+  a.k = k;
+  a.m = m;
+  a.parallelism = parallelism;
+  a.best_split = best_split;
+  a.max_depth = max_depth;
+  a.seed = seed;
+  a.tree_ids = tree_ids;
+  a.replay = replay;
+  et_forest *f = new et_forest();
+  f->ctx = ctx;
+  f->leaf_width = 1;
+  f->is_regression = 1;
+  try {
+    et_build_forest(ctx, D, a, f, stats);
+  } catch (...) {
+    delete f;
+    throw;
+  }
+  *out = f;
+  ET_API_END
+}
+
+// ---- forest ---------------------------------------------------------------------------------
+et_forest::~et_forest() {
+  if (ctx) cudaSetDevice(ctx->device);
+  if (d_tree_off) cudaFree(d_tree_off);
+  if (d_feature) cudaFree(d_feature);
+  if (d_cut) cudaFree(d_cut);
+  if (d_left) cudaFree(d_left);
+  if (d_right) cudaFree(d_right);
+  if (d_mil) cudaFree(d_mil);
+  if (d_leaf) cudaFree(d_leaf);
+}
+
+extern "C" void et_forest_free(et_forest *f) { delete f; }
+
+extern "C" int et_forest_dims(const et_forest *f, int32_t *m, int32_t *leaf_width, int32_t *is_regression,
+                              int64_t *total_nodes) {
+  if (!f) {
+    et_set_error("et_forest_dims: NULL forest");
+    return ET_EINVAL;
+  }
+  if (m) *m = (int32_t)f->trees.size();
+  if (leaf_width) *leaf_width = f->leaf_width;
+  if (is_regression) *is_regression = f->is_regression;
+  if (total_nodes) {
+    int64_t t = 0;
+    for (auto &tr : f->trees) t += (int64_t)tr.feature.size();
+    *total_nodes = t;
+  }
+  return ET_OK;
+}
+
+extern "C" int et_forest_tree_size(const et_forest *f, int32_t t, int32_t *n_nodes) {
+  if (!f || !n_nodes || t < 0 || t >= (int32_t)f->trees.size()) {
+    et_set_error("et_forest_tree_size: bad argument");
+    return ET_EINVAL;
+  }
+  *n_nodes = (int32_t)f->trees[(size_t)t].feature.size();
+  return ET_OK;
+}
+
+static void export_tree(const et_forest *f, const HostTree &tr, int32_t *feature, double *cut, uint8_t *mil,
+                        int32_t *left, int32_t *right, double *leaf) {
+  size_t n = tr.feature.size();
+  memcpy(feature, tr.feature.data(), n * sizeof(int32_t));
+  memcpy(cut, tr.cut.data(), n * sizeof(double));
+  memcpy(mil, tr.mil.data(), n);
+  memcpy(left, tr.left.data(), n * sizeof(int32_t));
+  memcpy(right, tr.right.data(), n * sizeof(int32_t));
+  memcpy(leaf, tr.leaf.data(), n * (size_t)f->leaf_width * sizeof(double));
+}
+
+extern "C" int et_forest_export(const et_forest *f, int32_t t, int32_t *feature, double *cut, uint8_t *mil,
+                                int32_t *left, int32_t *right, double *leaf) {
+  if (!f || t < 0 || t >= (int32_t)f->trees.size() || !feature || !cut || !mil || !left || !right || !leaf) {
+    et_set_error("et_forest_export: bad argument");
+    return ET_EINVAL;
+  }
+  export_tree(f, f->trees[(size_t)t], feature, cut, mil, left, right, leaf);
+  return ET_OK;
+}
+
+extern "C" int et_forest_export_all(const et_forest *f, int32_t *tree_sizes, int32_t *feature, double *cut,
+                                    uint8_t *mil, int32_t *left, int32_t *right, double *leaf) {
+  if (!f || !tree_sizes || !feature || !cut || !mil || !left || !right || !leaf) {
+    et_set_error("et_forest_export_all: bad argument");
+    return ET_EINVAL;
+  }
+  size_t off = 0;
+  for (size_t t = 0; t < f->trees.size(); t++) {
+    const HostTree &tr = f->trees[t];
+    tree_sizes[t] = (int32_t)tr.feature.size();
+    export_tree(f, tr, feature + off, cut + off, mil + off, left + off, right + off,
+                leaf + off * (size_t)f->leaf_width);
+    off += tr.feature.size();
+  }
+  return ET_OK;
+}
+
+extern "C" int et_forest_import(et_ctx *ctx, int32_t m, int32_t leaf_width, int32_t is_regression,
+                                const int32_t *tree_sizes, const int32_t *feature, const double *cut,
+                                const uint8_t *mil, const int32_t *left, const int32_t *right, const double *leaf,
+                                et_forest **out) {
+  ET_API_BEGIN
+  if (!ctx || !out || m < 0 || leaf_width <= 0) ET_FAIL(ET_EINVAL, "et_forest_import: bad argument");
+  if (m > 0 && (!tree_sizes || !feature || !cut || !mil || !left || !right || !leaf))
+    ET_FAIL(ET_EINVAL, "et_forest_import: NULL array");
+  et_forest *f = new et_forest();
+  f->ctx = ctx;
+  f->leaf_width = leaf_width;
+  f->is_regression = is_regression;
+  f->trees.resize((size_t)m);
+  size_t off = 0;
+  for (int32_t t = 0; t < m; t++) {
+    size_t n = (size_t)tree_sizes[t];
+    HostTree &tr = f->trees[(size_t)t];
+    tr.feature.assign(feature + off, feature + off + n);
+    tr.cut.assign(cut + off, cut + off + n);
+    tr.mil.assign(mil + off, mil + off + n);
+    tr.left.assign(left + off, left + off + n);
+    tr.right.assign(right + off, right + off + n);
+    tr.leaf.assign(leaf + off * (size_t)leaf_width, leaf + (off + n) * (size_t)leaf_width);
+    for (size_t i = 0; i < n; i++) {
+      if (tr.feature[i] >= 0 && (tr.left[i] <= (int32_t)i || tr.right[i] <= (int32_t)i || tr.left[i] >= (int32_t)n ||
+                                 tr.right[i] >= (int32_t)n)) {
+        delete f;
+        ET_FAIL(ET_EINVAL, "et_forest_import: tree %d node %zu has children outside pre-order range", t, i);
+      }
+    }
+    if (n == 0) {
+      delete f;
+      ET_FAIL(ET_EINVAL, "et_forest_import: tree %d is empty", t);
+    }
+    off += n;
+  }
+  *out = f;
+  ET_API_END
+}
+
+// ---- predict --------------------------------------------------------------------------------
+static void predict_host(et_ctx *ctx, et_forest *f, const double *x, int64_t n, int32_t d, double *out,
+                         int sum_only, int want_regression) {
+  if (!ctx || !f || (!x && n > 0 && d > 0) || (!out && n > 0)) ET_FAIL(ET_EINVAL, "predict: NULL argument");
+  if (f->is_regression != want_regression) ET_FAIL(ET_EINVAL, "predict: forest kind does not match the call");
+  if (n < 0 || d < 0) ET_FAIL(ET_EINVAL, "predict: negative dimensions");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (n == 0) return;
+  int lw = f->leaf_width;
+  // rows are streamed through the GPU in chunks: H2D, traverse, D2H
+  int64_t chunk = std::max<int64_t>(1, ((int64_t)512 << 20) / ((int64_t)std::max(d, 1) * 8));
+  chunk = std::min(chunk, n);
+  double *dx = nullptr, *dout = nullptr;
+  if (cudaMalloc((void **)&dx, (size_t)chunk * std::max(d, 1) * sizeof(double)) != cudaSuccess ||
+      cudaMalloc((void **)&dout, (size_t)chunk * lw * sizeof(double)) != cudaSuccess) {
+    cudaGetLastError();
+    if (dx) cudaFree(dx);
+    ET_FAIL(ET_ENOMEM, "predict: cannot allocate staging buffers");
+  }
+  try {
+    for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+      int64_t rows = std::min(chunk, n - r0);
+      if (d > 0)
+        CUDA_CHECK(cudaMemcpyAsync(dx, x + r0 * d, (size_t)rows * d * sizeof(double), cudaMemcpyHostToDevice,
+                                   ctx->stream));
+      et_predict_device_impl(ctx, f, dx, rows, d, dout, sum_only);
+      CUDA_CHECK(cudaMemcpyAsync(out + r0 * lw, dout, (size_t)rows * lw * sizeof(double), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+  } catch (...) {
+    cudaFree(dx);
+    cudaFree(dout);
+    throw;
+  }
+  cudaFree(dx);
+  cudaFree(dout);
+}
+
+extern "C" int et_predict_classification(et_ctx *ctx, et_forest *f, const double *x, int64_t n, int32_t d,
+                                         double *out, int32_t sum_only) {
+  ET_API_BEGIN
+  predict_host(ctx, f, x, n, d, out, sum_only, 0);
+  ET_API_END
+}
+extern "C" int et_predict_regression(et_ctx *ctx, et_forest *f, const double *x, int64_t n, int32_t d, double *out,
+                                     int32_t sum_only) {
+  ET_API_BEGIN
+  predict_host(ctx, f, x, n, d, out, sum_only, 1);
+  ET_API_END
+}
+
+static void predict_dev(et_ctx *ctx, et_forest *f, const double *x, int64_t n, int32_t d, double *out, int sum_only,
+                        int want_regression) {
+  if (!ctx || !f || (!x && n > 0 && d > 0) || (!out && n > 0)) ET_FAIL(ET_EINVAL, "predict: NULL argument");
+  if (f->is_regression != want_regression) ET_FAIL(ET_EINVAL, "predict: forest kind does not match the call");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (n <= 0) return;
+  et_predict_device_impl(ctx, f, x, n, d, out, sum_only);
+}
+
+extern "C" int et_predict_classification_device(et_ctx *ctx, et_forest *f, const double *x, int64_t n, int32_t d,
+                                                double *out, int32_t sum_only) {
+  ET_API_BEGIN
+  predict_dev(ctx, f, x, n, d, out, sum_only, 0);
+  ET_API_END
+}
+extern "C" int et_predict_regression_device(et_ctx *ctx, et_forest *f, const double *x, int64_t n, int32_t d,
+                                            double *out, int32_t sum_only) {
+  ET_API_BEGIN
+  predict_dev(ctx, f, x, n, d, out, sum_only, 1);
+  ET_API_END
+}

@@ -1,0 +1,203 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Replay mode (candidate features and threshold uniforms replayed from the reference's Cmwc5 stream):
+tree structure, cutpoints and leaf values must be BIT-EXACT (the north star allows 1e-12 relative on
+leaf values; these tests hold them to 0).  Free-running mode: accuracy/RMSE properties."""
+import numpy as np
+import pytest
+
+import lamp_b200 as et
+from oracle import oracle as O
+from tests.helpers import (assert_trees_bit_exact, oracle_replay, synth_classification, synth_regression)
+
+pytestmark = pytest.mark.gpu
+NAN = float("nan")
+
+
+# ---- predict ----------------------------------------------------------------------------------------
+def test_predict_classification_matches_oracle(mnist):
+    x, y = mnist
+    of = O.build_forest_classification(x[:3000], y[:3000], None, 10, 2, 28, 7, 4, seed=3)
+    gf = et.Forest.from_trees(of.trees())
+    p_gpu = et.predictClassification(gf, x[3000:5000])
+    p_ora = of.predict(x[3000:5000])
+    assert np.array_equal(p_gpu, p_ora)  # same additions in tree order, same division
+
+
+def test_predict_regression_matches_oracle():
+    x, y = synth_regression(4000, 12, 1, nan_frac=0.02)
+    of = O.build_forest_regression(x, y, 5, 4, 9, 4, seed=5)
+    gf = et.Forest.from_trees(of.trees())
+    assert np.array_equal(et.predictRegression(gf, x), of.predict(x))
+
+
+def test_predict_accepts_adt_trees():
+    leaf = et.ClassificationLeaf
+    t = et.ClassificationNonLeaf(leaf((1.0, 0.0)), leaf((0.0, 1.0)), 0, 1.0, True)
+    x = np.array([[0.5], [1.5], [NAN]])
+    assert et.predictClassification([t, t], x).tolist() == [[1.0, 0.0], [0.0, 1.0], [1.0, 0.0]]
+
+
+# ---- replay: classification ----------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,seed,k", [(2000, 0, 32), (2000, 42, 32), (10000, 0, 32), (10000, 7, 28), (3000, 5, 1)])
+def test_replay_mnist_classification(mnist, rows, seed, k):
+    x, y = mnist
+    x, y = x[:rows], y[:rows]
+    of = O.build_forest_classification(x, y, None, 10, 2, k, 1, 1, max_depth=200, seed=seed, record_trace=True)
+    gf = et.buildForestClassification(x, y, None, 10, 2, k, 1, 1, maxDepth=200, seed=seed, replay=oracle_replay(of))
+    assert_trees_bit_exact(gf, of)
+    so, sg = of.stats(), gf.stats
+    for key in ("v_mm", "v_sc", "s_rows", "p_rows", "draws", "const_hits", "scored", "nodes"):
+        assert so[key] == sg[key], (key, so[key], sg[key])
+
+
+def test_replay_forest_parallel_seeding(mnist):
+    x, y = mnist
+    x, y = x[:1500], y[:1500]
+    of = O.build_forest_classification(x, y, None, 10, 2, 28, 12, 4, seed=99, record_trace=True)
+    gf = et.buildForestClassification(x, y, None, 10, 2, 28, 12, 4, seed=99, replay=oracle_replay(of))
+    assert_trees_bit_exact(gf, of)
+    assert np.array_equal(et.predictClassification(gf, x), of.predict(x))
+
+
+@pytest.mark.parametrize("nan_frac,max_depth,n_min", [(0.0, 2**31 - 1, 2), (0.05, 2**31 - 1, 2), (0.3, 6, 2)])
+def test_replay_synthetic_classification(nan_frac, max_depth, n_min):
+    x, y = synth_classification(5000, 20, 4, 11, nan_frac=nan_frac, const_cols=3, quantize=4)
+    of = O.build_forest_classification(x, y, None, 4, n_min, 5, 6, 2, max_depth=max_depth, seed=1, record_trace=True)
+    gf = et.buildForestClassification(x, y, None, 4, n_min, 5, 6, 2, maxDepth=max_depth, seed=1,
+                                      replay=oracle_replay(of))
+    assert_trees_bit_exact(gf, of)
+
+
+def test_replay_all_nan_column_and_nmin_quirk():
+    # all-NaN column: min=MaxValue, max=MinValue, cut=-inf/NaN -> NaN score -> "constant" (pkg:283-285)
+    x, y = synth_classification(400, 5, 2, 3)
+    x[:, 2] = NAN
+    of = O.build_forest_classification(x, y, None, 2, 2, 3, 5, 2, seed=4, record_trace=True)
+    gf = et.buildForestClassification(x, y, None, 2, 2, 3, 5, 2, seed=4, replay=oracle_replay(of))
+    assert_trees_bit_exact(gf, of)
+    # pkg:993: nMin compares the WHOLE TABLE's rows: nMin > n makes every root a leaf
+    of = O.build_forest_classification(x, y, None, 2, 401, 3, 2, 2, seed=4, record_trace=True)
+    gf = et.buildForestClassification(x, y, None, 2, 401, 3, 2, 2, seed=4, replay=oracle_replay(of))
+    assert_trees_bit_exact(gf, of)
+    assert gf.flat(0).n_nodes == 1
+
+
+# ---- replay: weighted classification ---------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["half_zero", "real"])
+def test_replay_weighted_classification(mnist, kind):
+    x, y = mnist
+    x, y = x[:2000], y[:2000]
+    if kind == "half_zero":  # tst:357-395
+        w = np.concatenate([np.ones(1000), np.zeros(1000)])
+    else:
+        w = np.random.default_rng(0).gamma(2.0, size=2000)
+    of = O.build_forest_classification(x, y, w, 10, 2, 32, 2, 8, max_depth=200, seed=13, record_trace=True)
+    gf = et.buildForestClassification(x, y, w, 10, 2, 32, 2, 8, maxDepth=200, seed=13, replay=oracle_replay(of))
+    assert_trees_bit_exact(gf, of)
+
+
+# ---- replay: regression ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,seed", [(2000, 0), (2000, 42), (10000, 0)])
+def test_replay_mnist_regression(mnist, rows, seed):
+    x, y = mnist
+    x, y = x[:rows], y[:rows].astype(np.float64)
+    of = O.build_forest_regression(x, y, 2, 32, 1, 1, max_depth=200, seed=seed, record_trace=True)
+    gf = et.buildForestRegression(x, y, 2, 32, 1, 1, maxDepth=200, seed=seed, replay=oracle_replay(of))
+    assert_trees_bit_exact(gf, of)
+
+
+@pytest.mark.parametrize("nan_frac,max_depth,n_min", [(0.0, 2**31 - 1, 5), (0.1, 2**31 - 1, 2), (0.0, 4, 2)])
+def test_replay_synthetic_regression(nan_frac, max_depth, n_min):
+    x, y = synth_regression(6000, 15, 2, nan_frac=nan_frac)
+    of = O.build_forest_regression(x, y, n_min, 4, 5, 3, max_depth=max_depth, seed=8, record_trace=True)
+    gf = et.buildForestRegression(x, y, n_min, 4, 5, 3, maxDepth=max_depth, seed=8, replay=oracle_replay(of))
+    assert_trees_bit_exact(gf, of)
+    assert np.array_equal(et.predictRegression(gf, x), of.predict(x))
+
+
+# ---- free-running: the reference's own property tests --------------------------------------------------
+def test_free_mnist_one_tree_fits_training_set(mnist):  # tst:283-319
+    x, y = mnist
+    f = et.buildForestClassification(x, y, None, 10, 2, 32, 1, 1, maxDepth=200, seed=1)
+    assert (et.predictClassification(f, x).argmax(1) == y).mean() == 1.0
+
+
+def test_free_mnist_regression_fits_training_set(mnist):  # tst:442-477
+    x, y = mnist
+    f = et.buildForestRegression(x, y.astype(np.float64), 2, 32, 1, 8, maxDepth=200, seed=2)
+    assert np.array_equal(et.predictRegression(f, x).astype(np.int64), y)
+
+
+def test_free_mnist_weighted(mnist):  # tst:357-395
+    x, y = mnist
+    w = np.concatenate([np.ones(5000), np.zeros(5000)])
+    f = et.buildForestClassification(x, y, w, 10, 2, 32, 1, 8, maxDepth=200, seed=3)
+    acc = (et.predictClassification(f, x).argmax(1) == y).mean()
+    assert 0.5 < acc <= 0.9
+    assert (et.predictClassification(f, x[:5000]).argmax(1) == y[:5000]).mean() == 1.0
+
+
+def test_free_missing_regression():  # tst:515-533
+    x = np.array([[1.0], [1.0], [1.0], [1.0], [NAN], [NAN], [NAN]])
+    y = np.array([1.0, 1, 1, 1, 0, 0, 0])
+    f = et.buildForestRegression(x, y, 1, 1, 100, 1, maxDepth=200, seed=1)
+    assert np.array_equal(et.predictRegression(f, x), y)
+    t = f[0]
+    assert isinstance(t, et.RegressionNonLeaf) and t.splitFeature == 0 and t.cutpoint == 1.0 and t.splitMissingIsLess
+    assert t.left == et.RegressionLeaf(0.0) and t.right == et.RegressionLeaf(1.0)
+
+
+def test_free_missing_classification():  # tst:534-554
+    x = np.array([[1.0], [1.0], [1.0], [1.0], [NAN], [NAN], [NAN]])
+    y = np.array([1, 1, 1, 1, 0, 0, 0], np.int32)
+    f = et.buildForestClassification(x, y, None, 2, 1, 1, 100, 1, maxDepth=200, seed=1)
+    assert np.array_equal(et.predictClassification(f, x)[:, 1], y.astype(np.float64))
+
+
+def test_free_accuracy_close_to_oracle(mnist):
+    """Free-running tolerance: held-out accuracy of a 30-tree GPU forest within 2 points of the
+    oracle's (reference algorithm, Cmwc5 stream) on the same split."""
+    x, y = mnist
+    xtr, ytr, xte, yte = x[:6000], y[:6000], x[6000:], y[6000:]
+    of = O.build_forest_classification(xtr, ytr, None, 10, 2, 28, 30, 8, seed=5)
+    gf = et.buildForestClassification(xtr, ytr, None, 10, 2, 28, 30, 8, seed=5)
+    acc_o = (of.predict(xte).argmax(1) == yte).mean()
+    acc_g = (et.predictClassification(gf, xte).argmax(1) == yte).mean()
+    assert abs(acc_o - acc_g) < 0.02, (acc_o, acc_g)
+    assert acc_g > 0.9
+    # same amount of work: nodes per tree within 5%
+    assert abs(gf.stats["nodes"] / of.stats()["nodes"] - 1) < 0.05
+
+
+def test_free_rmse_close_to_oracle():
+    x, y = synth_regression(12000, 20, 5)
+    xtr, ytr, xte, yte = x[:8000], y[:8000], x[8000:], y[8000:]
+    of = O.build_forest_regression(xtr, ytr, 5, 5, 30, 8, seed=6)
+    gf = et.buildForestRegression(xtr, ytr, 5, 5, 30, 8, seed=6)
+    rm_o = np.sqrt(np.mean((of.predict(xte) - yte) ** 2))
+    rm_g = np.sqrt(np.mean((et.predictRegression(gf, xte) - yte) ** 2))
+    assert abs(rm_o - rm_g) / rm_o < 0.05, (rm_o, rm_g)
+
+
+def test_free_determinism_and_tree_ids(mnist):
+    """A tree's stream depends only on (seed, tree id): shards rebuild the same trees."""
+    x, y = mnist
+    x, y = x[:1500], y[:1500]
+    full = et.buildForestClassification(x, y, None, 10, 2, 16, 6, 4, seed=21)
+    odd = et.buildForestClassification(x, y, None, 10, 2, 16, 3, 4, seed=21, tree_ids=[1, 3, 5])
+    for j, t in enumerate([1, 3, 5]):
+        a, b = full.flat(t), odd.flat(j)
+        assert np.array_equal(a.feature, b.feature) and np.array_equal(a.cut.view(np.int64), b.cut.view(np.int64))
+        assert np.array_equal(a.leaf, b.leaf)
+
+
+# ---- argument errors mirror the reference's require(...) -------------------------------------------------
+def test_require_failures():
+    x = np.zeros((4, 2))
+    with pytest.raises(ValueError):  # pkg:624-627
+        et.buildForestClassification(x, np.zeros(3, np.int32), None, 2, 2, 1, 1, 1)
+    with pytest.raises(ValueError):  # pkg:631-633
+        et.buildForestClassification(x, np.zeros(4, np.int32), [1.0, -1.0, 1.0, 1.0], 2, 2, 1, 1, 1)
+    with pytest.raises(ValueError):  # pkg:715-718
+        et.buildForestRegression(x, np.zeros(5), 2, 1, 1, 1)
