@@ -299,16 +299,16 @@ class Forest(Sequence):
         return Forest(ctx, h)
 
     @staticmethod
-    def from_trees(trees, ctx: Optional[Context] = None) -> "Forest":
+    def from_trees(trees, ctx: Optional[Context] = None, regression_hint: bool = False) -> "Forest":
         """Seq of nested ADT trees or FlatTrees -> device forest (the reference's predict input)."""
         trees = list(trees)
         if not trees:
             raise ValueError("empty forest")
         first = trees[0]
-        if isinstance(first, FlatTree):
+        if hasattr(first, "feature") and hasattr(first, "leaf"):  # FlatTree-like (pre-order arrays)
             flats = trees
             lw = first.leaf.shape[1]
-            regression = None
+            regression = regression_hint
         else:
             regression = isinstance(first, (RegressionLeaf, RegressionNonLeaf))
             lw = 1 if regression else len(_first_leaf(first).targetDistribution)

@@ -27,7 +27,7 @@ def test_predict_classification_matches_oracle(mnist):
 def test_predict_regression_matches_oracle():
     x, y = synth_regression(4000, 12, 1, nan_frac=0.02)
     of = O.build_forest_regression(x, y, 5, 4, 9, 4, seed=5)
-    gf = et.Forest.from_trees(of.trees())
+    gf = et.Forest.from_trees(of.trees(), regression_hint=True)
     assert np.array_equal(et.predictRegression(gf, x), of.predict(x))
 
 
