@@ -235,7 +235,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = et.Context(local)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real (non-null) stream shared by torch's events and the library's kernels
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     x, y = make_data(cfg)  # identical on every rank (same seed): the table is replicated per GPU

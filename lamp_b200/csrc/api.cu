@@ -2,6 +2,7 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <memory>
 
 #include "internal.h"
 
@@ -62,6 +63,7 @@ extern "C" void et_shutdown(et_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  et_workspace_free(ctx->ws);
   delete ctx;
 }
 
@@ -343,6 +345,7 @@ extern "C" int et_build_classification(et_ctx *ctx, et_data *D, const int32_t *t
   f->ctx = ctx;
   f->leaf_width = num_classes;
   f->is_regression = 0;
+  f->m = m;
   try {
     et_build_forest(ctx, D, a, f, stats);
   } catch (...) {
@@ -383,6 +386,7 @@ extern "C" int et_build_regression(et_ctx *ctx, et_data *D, const double *target
   f->ctx = ctx;
   f->leaf_width = 1;
   f->is_regression = 1;
+  f->m = m;
   try {
     et_build_forest(ctx, D, a, f, stats);
   } catch (...) {
@@ -397,15 +401,30 @@ extern "C" int et_build_regression(et_ctx *ctx, et_data *D, const double *target
 et_forest::~et_forest() {
   if (ctx) cudaSetDevice(ctx->device);
   if (d_tree_off) cudaFree(d_tree_off);
-  if (d_feature) cudaFree(d_feature);
-  if (d_cut) cudaFree(d_cut);
-  if (d_left) cudaFree(d_left);
-  if (d_right) cudaFree(d_right);
-  if (d_mil) cudaFree(d_mil);
+  if (d_nodes) cudaFree(d_nodes);
   if (d_leaf) cudaFree(d_leaf);
 }
 
 extern "C" void et_forest_free(et_forest *f) { delete f; }
+
+// The forest lives in HBM; the host copy is fetched on first export.
+void et_forest_fetch(et_forest *f) {
+  if (f->host_ready) return;
+  std::lock_guard<std::mutex> lk(f->ctx->mu);
+  if (f->host_ready) return;
+  CUDA_CHECK(cudaSetDevice(f->ctx->device));
+  f->h_nodes.resize((size_t)f->total_nodes);
+  f->h_leaf.resize((size_t)f->total_leaves * (size_t)f->leaf_width);
+  cudaStream_t st = f->ctx->stream;
+  if (f->total_nodes)
+    CUDA_CHECK(cudaMemcpyAsync(f->h_nodes.data(), f->d_nodes, f->h_nodes.size() * sizeof(PNode),
+                               cudaMemcpyDeviceToHost, st));
+  if (!f->h_leaf.empty())
+    CUDA_CHECK(cudaMemcpyAsync(f->h_leaf.data(), f->d_leaf, f->h_leaf.size() * sizeof(double), cudaMemcpyDeviceToHost,
+                               st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  f->host_ready = true;
+}
 
 extern "C" int et_forest_dims(const et_forest *f, int32_t *m, int32_t *leaf_width, int32_t *is_regression,
                               int64_t *total_nodes) {
@@ -413,62 +432,71 @@ extern "C" int et_forest_dims(const et_forest *f, int32_t *m, int32_t *leaf_widt
     et_set_error("et_forest_dims: NULL forest");
     return ET_EINVAL;
   }
-  if (m) *m = (int32_t)f->trees.size();
+  if (m) *m = f->m;
   if (leaf_width) *leaf_width = f->leaf_width;
   if (is_regression) *is_regression = f->is_regression;
-  if (total_nodes) {
-    int64_t t = 0;
-    for (auto &tr : f->trees) t += (int64_t)tr.feature.size();
-    *total_nodes = t;
-  }
+  if (total_nodes) *total_nodes = f->total_nodes;
   return ET_OK;
 }
 
 extern "C" int et_forest_tree_size(const et_forest *f, int32_t t, int32_t *n_nodes) {
-  if (!f || !n_nodes || t < 0 || t >= (int32_t)f->trees.size()) {
+  if (!f || !n_nodes || t < 0 || t >= f->m) {
     et_set_error("et_forest_tree_size: bad argument");
     return ET_EINVAL;
   }
-  *n_nodes = (int32_t)f->trees[(size_t)t].feature.size();
+  *n_nodes = (int32_t)(f->tree_off[(size_t)t + 1] - f->tree_off[(size_t)t]);
   return ET_OK;
 }
 
-static void export_tree(const et_forest *f, const HostTree &tr, int32_t *feature, double *cut, uint8_t *mil,
-                        int32_t *left, int32_t *right, double *leaf) {
-  size_t n = tr.feature.size();
-  memcpy(feature, tr.feature.data(), n * sizeof(int32_t));
-  memcpy(cut, tr.cut.data(), n * sizeof(double));
-  memcpy(mil, tr.mil.data(), n);
-  memcpy(left, tr.left.data(), n * sizeof(int32_t));
-  memcpy(right, tr.right.data(), n * sizeof(int32_t));
-  memcpy(leaf, tr.leaf.data(), n * (size_t)f->leaf_width * sizeof(double));
+static void export_tree(const et_forest *f, int32_t t, int32_t *feature, double *cut, uint8_t *mil, int32_t *left,
+                        int32_t *right, double *leaf) {
+  const int64_t off = f->tree_off[(size_t)t];
+  const int64_t n = f->tree_off[(size_t)t + 1] - off;
+  const int lw = f->leaf_width;
+  for (int64_t i = 0; i < n; i++) {
+    const PNode p = f->h_nodes[(size_t)(off + i)];
+    if (p.feat >= 0) {
+      feature[i] = p.feat & (ET_MIL_BIT - 1);
+      mil[i] = (p.feat & ET_MIL_BIT) ? 1 : 0;
+      cut[i] = p.cut;
+      left[i] = (int32_t)i + 1;
+      right[i] = p.right_or_leaf;
+      for (int c = 0; c < lw; c++) leaf[i * lw + c] = 0.0;
+    } else {
+      feature[i] = -1;
+      mil[i] = 0;
+      cut[i] = NAN;
+      left[i] = -1;
+      right[i] = -1;
+      const double *lv = f->h_leaf.data() + (size_t)p.right_or_leaf * (size_t)lw;
+      for (int c = 0; c < lw; c++) leaf[i * lw + c] = lv[c];
+    }
+  }
 }
 
 extern "C" int et_forest_export(const et_forest *f, int32_t t, int32_t *feature, double *cut, uint8_t *mil,
                                 int32_t *left, int32_t *right, double *leaf) {
-  if (!f || t < 0 || t >= (int32_t)f->trees.size() || !feature || !cut || !mil || !left || !right || !leaf) {
-    et_set_error("et_forest_export: bad argument");
-    return ET_EINVAL;
-  }
-  export_tree(f, f->trees[(size_t)t], feature, cut, mil, left, right, leaf);
-  return ET_OK;
+  ET_API_BEGIN
+  if (!f || t < 0 || t >= f->m || !feature || !cut || !mil || !left || !right || !leaf)
+    ET_FAIL(ET_EINVAL, "et_forest_export: bad argument");
+  et_forest_fetch(const_cast<et_forest *>(f));
+  export_tree(f, t, feature, cut, mil, left, right, leaf);
+  ET_API_END
 }
 
 extern "C" int et_forest_export_all(const et_forest *f, int32_t *tree_sizes, int32_t *feature, double *cut,
                                     uint8_t *mil, int32_t *left, int32_t *right, double *leaf) {
-  if (!f || !tree_sizes || !feature || !cut || !mil || !left || !right || !leaf) {
-    et_set_error("et_forest_export_all: bad argument");
-    return ET_EINVAL;
-  }
-  size_t off = 0;
-  for (size_t t = 0; t < f->trees.size(); t++) {
-    const HostTree &tr = f->trees[t];
-    tree_sizes[t] = (int32_t)tr.feature.size();
-    export_tree(f, tr, feature + off, cut + off, mil + off, left + off, right + off,
+  ET_API_BEGIN
+  if (!f || !tree_sizes || !feature || !cut || !mil || !left || !right || !leaf)
+    ET_FAIL(ET_EINVAL, "et_forest_export_all: bad argument");
+  et_forest_fetch(const_cast<et_forest *>(f));
+  for (int32_t t = 0; t < f->m; t++) {
+    size_t off = (size_t)f->tree_off[(size_t)t];
+    tree_sizes[t] = (int32_t)(f->tree_off[(size_t)t + 1] - f->tree_off[(size_t)t]);
+    export_tree(f, t, feature + off, cut + off, mil + off, left + off, right + off,
                 leaf + off * (size_t)f->leaf_width);
-    off += tr.feature.size();
   }
-  return ET_OK;
+  ET_API_END
 }
 
 extern "C" int et_forest_import(et_ctx *ctx, int32_t m, int32_t leaf_width, int32_t is_regression,
@@ -479,35 +507,58 @@ extern "C" int et_forest_import(et_ctx *ctx, int32_t m, int32_t leaf_width, int3
   if (!ctx || !out || m < 0 || leaf_width <= 0) ET_FAIL(ET_EINVAL, "et_forest_import: bad argument");
   if (m > 0 && (!tree_sizes || !feature || !cut || !mil || !left || !right || !leaf))
     ET_FAIL(ET_EINVAL, "et_forest_import: NULL array");
-  et_forest *f = new et_forest();
+  std::unique_ptr<et_forest> f(new et_forest());
   f->ctx = ctx;
   f->leaf_width = leaf_width;
   f->is_regression = is_regression;
-  f->trees.resize((size_t)m);
-  size_t off = 0;
+  f->m = m;
+  f->tree_off.assign((size_t)m + 1, 0);
   for (int32_t t = 0; t < m; t++) {
-    size_t n = (size_t)tree_sizes[t];
-    HostTree &tr = f->trees[(size_t)t];
-    tr.feature.assign(feature + off, feature + off + n);
-    tr.cut.assign(cut + off, cut + off + n);
-    tr.mil.assign(mil + off, mil + off + n);
-    tr.left.assign(left + off, left + off + n);
-    tr.right.assign(right + off, right + off + n);
-    tr.leaf.assign(leaf + off * (size_t)leaf_width, leaf + (off + n) * (size_t)leaf_width);
-    for (size_t i = 0; i < n; i++) {
-      if (tr.feature[i] >= 0 && (tr.left[i] <= (int32_t)i || tr.right[i] <= (int32_t)i || tr.left[i] >= (int32_t)n ||
-                                 tr.right[i] >= (int32_t)n)) {
-        delete f;
-        ET_FAIL(ET_EINVAL, "et_forest_import: tree %d node %zu has children outside pre-order range", t, i);
-      }
-    }
-    if (n == 0) {
-      delete f;
-      ET_FAIL(ET_EINVAL, "et_forest_import: tree %d is empty", t);
-    }
-    off += n;
+    if (tree_sizes[t] <= 0) ET_FAIL(ET_EINVAL, "et_forest_import: tree %d is empty", t);
+    f->tree_off[(size_t)t + 1] = f->tree_off[(size_t)t] + tree_sizes[t];
   }
-  *out = f;
+  f->total_nodes = f->tree_off[(size_t)m];
+  f->h_nodes.resize((size_t)f->total_nodes);
+  int64_t n_leaves = 0;
+  for (int32_t t = 0; t < m; t++) {
+    const int64_t off = f->tree_off[(size_t)t], n = tree_sizes[t];
+    for (int64_t i = 0; i < n; i++) {
+      PNode p;
+      p.cut = cut[off + i];
+      if (feature[off + i] >= 0) {
+        // pre-order: left child directly follows its parent, right child lies further on
+        if (left[off + i] != i + 1 || right[off + i] <= i + 1 || right[off + i] >= n)
+          ET_FAIL(ET_EINVAL, "et_forest_import: tree %d node %lld is not in pre-order", t, (long long)i);
+        if (feature[off + i] >= ET_MIL_BIT) ET_FAIL(ET_EINVAL, "et_forest_import: feature index too large");
+        p.feat = feature[off + i] | (mil[off + i] ? ET_MIL_BIT : 0);
+        p.right_or_leaf = right[off + i];
+      } else {
+        if (n_leaves >= 0x7fffffff) ET_FAIL(ET_EUNSUPPORTED, "et_forest_import: more than 2^31 leaves");
+        p.feat = -1;
+        p.right_or_leaf = (int32_t)n_leaves++;
+        for (int c = 0; c < leaf_width; c++) f->h_leaf.push_back(leaf[(off + i) * leaf_width + c]);
+      }
+      f->h_nodes[(size_t)(off + i)] = p;
+    }
+  }
+  f->total_leaves = n_leaves;
+  f->host_ready = true;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  CUDA_CHECK(cudaMalloc((void **)&f->d_tree_off, ((size_t)m + 1) * sizeof(int64_t)));
+  CUDA_CHECK(cudaMalloc((void **)&f->d_nodes, std::max<size_t>(1, (size_t)f->total_nodes) * sizeof(PNode)));
+  CUDA_CHECK(cudaMalloc((void **)&f->d_leaf, std::max<size_t>(1, f->h_leaf.size()) * sizeof(double)));
+  cudaStream_t st = ctx->stream;
+  CUDA_CHECK(cudaMemcpyAsync(f->d_tree_off, f->tree_off.data(), ((size_t)m + 1) * sizeof(int64_t),
+                             cudaMemcpyHostToDevice, st));
+  if (f->total_nodes)
+    CUDA_CHECK(cudaMemcpyAsync(f->d_nodes, f->h_nodes.data(), f->h_nodes.size() * sizeof(PNode),
+                               cudaMemcpyHostToDevice, st));
+  if (!f->h_leaf.empty())
+    CUDA_CHECK(cudaMemcpyAsync(f->d_leaf, f->h_leaf.data(), f->h_leaf.size() * sizeof(double), cudaMemcpyHostToDevice,
+                               st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  *out = f.release();
   ET_API_END
 }
 

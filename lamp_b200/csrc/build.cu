@@ -5,21 +5,27 @@
 // (pkg:427-511) of extratrees/src/main/scala/lamp/forest/package.scala.
 //
 // Data layout in HBM
-//   X        column-major FP64 [d][ld]              (the JVM walks a row-major matrix with stride d)
-//   idx      int32 [B][n] x2 (ping-pong)            sample rows of every open node, ascending inside a
-//                                                   node segment (the reference's filter keeps order)
-//   yc/yr/w  labels / targets / weights permuted alongside idx so a node's segment streams
-//   frontier SoA of open nodes (tree, begin, end, node id, depth, RNG key | trace node, class hist)
-//   cand     SoA of candidate (node, feature) pairs of the current round
+//   X         column-major FP64 [d][ld]            (the JVM walks a row-major matrix with stride d)
+//   idx       int32 [B][n] x2 (ping-pong)          sample rows of every open node, ascending inside a
+//                                                  node segment (the reference's filter keeps order)
+//   yc/yr/w   labels / targets / weights permuted alongside idx so a node's segment streams
+//   frontier  SoA of the open nodes of one level (tree, begin, end, node id, depth, RNG key | trace
+//             node, class histogram, known-constant feature bitmask), x2 (this level / next level)
+//   queues    frontier indices bucketed by node size: small nodes -> one warp per node,
+//             large nodes -> one CTA per node
+//   pool      output nodes in creation (level) order + compact leaf-value pool; converted on the
+//             device to per-tree pre-order 16-byte nodes (the layout predict traverses)
 //
-// One level = classify (stop rules) -> rounds of { draw candidates ; min/max + threshold score } ->
-// finalize (first-best argmax already folded into the rounds) -> stable partition.
+// One level = one launch per size class.  A team (warp or CTA) owns a node end to end: stop rules,
+// split search (batches of candidates: gather + min/max + cutpoint + side histogram with the whole
+// team on the samples of one candidate, then one thread per candidate for the exact score), first-
+// best argmax, stable partition, children.  The host only reads the next level's queue sizes.
 //
 // Exactness: every floating-point expression of the reference is evaluated with individually
 // rounded _rn operations in the reference's order.  Unweighted classification reduces integer
-// class histograms in parallel (exact) and evaluates the Gini expressions in one thread; weighted
-// classification and regression sum in subset order (sequential chains, one thread per candidate,
-// massively parallel across candidates/nodes/trees) because FP addition is not associative.
+// class histograms in parallel (exact) and evaluates the Gini expressions in one thread per
+// candidate; weighted classification and regression sum in subset order (sequential chains, one
+// thread per candidate) because FP addition is not associative.
 #include <algorithm>
 #include <chrono>
 
@@ -28,58 +34,34 @@
 namespace {
 
 enum { TASK_CLS = 0, TASK_CLSW = 1, TASK_REG = 2 };
-enum { FLAG_SEARCH = 0, FLAG_LEAF = 1, FLAG_DONE = 2 };
-enum { CF_CONST = 1, CF_NAN = 2 };
+enum { CF_CONST = 1, CF_NAN = 2, CF_MIL = 4 };
+enum { ST_VMM = 0, ST_VSC, ST_SROWS, ST_PROWS, ST_DRAWS, ST_CONST, ST_SCORED, ST_MISMATCH, ST_COUNT };
 
-enum {
-  ST_VMM = 0,
-  ST_VSC,
-  ST_SROWS,
-  ST_PROWS,
-  ST_DRAWS,
-  ST_CONST,
-  ST_SCORED,
-  ST_MISMATCH,
-  ST_COUNT
-};
+constexpr int NW_MAX = 1024;      // nodes up to this many samples are owned by one warp
+constexpr int BITS_W = NW_MAX / 32;
+constexpr int CTA_TEAM = 512;     // threads of the CTA that owns a larger node
+constexpr int WARPS_PER_CTA = 4;  // warp teams per CTA in the small-node kernel
 
 struct Counters {
-  int32_t n_cand[2];
   int32_t next_f;
-  int32_t pad;
-  unsigned long long mask_words;
+  int32_t q_count[2];
+  int32_t n_leaves;
+  unsigned long long scratch_words;
   unsigned long long st[ST_COUNT];
 };
 
-struct Level {  // frontier of one level
+struct Frontier {
   int32_t *tree, *begin, *end, *node, *depth;
   int64_t *trace;
   uint64_t *key;
-  int32_t *hist;   // [F][C]   (TASK_CLS)
-  uint32_t *mask;  // [F][W]   (free-running: known-constant | taken features)
+  int32_t *hist;   // [F][C]  (TASK_CLS)
+  uint32_t *mask;  // [F][W]  (free-running: features known constant on the path from the root)
 };
 
-struct Search {  // per frontier node, valid within one level
-  uint8_t *flag, *best_mil;
-  int32_t *visited, *nconst, *dc, *cand_begin, *cand_cnt, *best_feature, *best_nleft, *split_slot;
-  double *best_score, *best_cut, *total, *nsum, *mean;
-  int32_t *scored;   // [F][k] features scored at this node (their mask bits are not inherited)
-  int32_t *best_hl;  // [F][C] class histogram of the best candidate's left side (TASK_CLS)
-  double *dist;      // [F][C] weighted class distribution (TASK_CLSW)
-};
-
-struct Cand {  // per candidate of one round
-  int32_t *node, *feature, *cnt_lt, *cnt_nan;
-  double *u, *cut, *score;
-  uint8_t *flags, *mil;
-  int32_t *hist;      // [cand][2][C]  (TASK_CLS): <cut histogram, NaN histogram
-  int64_t *mask_off;  // word offset of the side bitmasks (TASK_CLSW / TASK_REG)
-};
-
-struct Out {
-  int32_t *feature, *left, *right;
-  double *cut, *leaf;
-  uint8_t *mil;
+struct Pool {  // output nodes in creation order
+  int32_t *tree, *feat, *child;  // feat: -1 leaf | feature + MIL bit; child: left child id | leaf slot
+  double *cut;
+  double *leaf_vals;  // [leaf slot][lw]
 };
 
 struct Trace {
@@ -89,26 +71,69 @@ struct Trace {
   const uint8_t *cand_flag;
 };
 
-struct P {  // kernel parameters shared by all kernels of a batch
-  const double *X;
-  int64_t ld, n, n_table;
-  int32_t d, C, k, n_min, max_depth, W, task, replay;
-  int32_t *idx_src, *idx_dst, *yc_src, *yc_dst;
-  double *yr_src, *yr_dst, *w_src, *w_dst;
-  Level cur, nxt;
-  Search s;
-  Cand c[2];
-  Out o;
-  Trace tr;
-  Counters *cnt;
-  uint32_t *sidemask;  // bitmask scratch (TASK_CLSW / TASK_REG)
-  double *wscratch;    // [cand][2][2][C] weighted histograms
-  int32_t node_base_next;
+// shared-memory layout of one team (identical on host and device)
+struct Lay {
+  int o_u, o_cut, o_score, o_dist, o_redd, o_wh;                                            // doubles
+  int o_feat, o_flags, o_nleft, o_hnode, o_besthl, o_hist, o_redi, o_mask, o_bits, o_misc;  // int32
+  int hs;  // stride of one candidate's histogram row (odd: conflict-free per-candidate reads)
+  int bytes;
 };
 
-__device__ __forceinline__ void stat_add(const P &p, int which, unsigned long long v) {
-  atomicAdd(&p.cnt->st[which], v);
+__host__ __device__ inline Lay make_lay(int task, bool warp_team, int C, int NB, int W, bool replay) {
+  Lay L;
+  int o = 0;  // in 8-byte units first
+  L.o_u = o;
+  o += NB;
+  L.o_cut = o;
+  o += NB;
+  L.o_score = o;
+  o += NB + 1;
+  L.o_dist = o;
+  o += (task == TASK_REG) ? 0 : C;
+  L.o_redd = o;
+  o += warp_team ? 0 : 64;
+  L.o_wh = o;
+  o += (task == TASK_CLSW) ? NB * 2 * C : 0;
+  int oi = o * 2;  // switch to 4-byte units
+  L.hs = (2 * C) | 1;
+  L.o_feat = oi;
+  oi += NB;
+  L.o_flags = oi;
+  oi += NB;
+  L.o_nleft = oi;
+  oi += NB;
+  L.o_hnode = oi;
+  oi += (task == TASK_CLS) ? C : 0;
+  L.o_besthl = oi;
+  oi += (task == TASK_CLS) ? C : 0;
+  L.o_hist = oi;
+  oi += (task == TASK_CLS) ? NB * L.hs : 0;
+  L.o_redi = oi;
+  oi += warp_team ? 0 : 128;
+  L.o_mask = oi;
+  oi += replay ? 0 : 2 * W;
+  L.o_bits = oi;
+  oi += (task != TASK_CLS && warp_team) ? NB * 2 * BITS_W : 0;
+  L.o_misc = oi;
+  oi += 8;
+  L.bytes = ((oi + 3) / 4) * 16;
+  return L;
 }
+
+struct P {
+  const double *X;
+  int64_t ld, n, n_table;
+  int32_t d, C, k, n_min, max_depth, W, task, replay, NB;
+  int32_t *idx_src, *idx_dst, *yc_src, *yc_dst;
+  double *yr_src, *yr_dst, *w_src, *w_dst;
+  Frontier cur, nxt;
+  int32_t *q_cur[2], *q_nxt[2];
+  Pool o;
+  Trace tr;
+  Counters *cnt;
+  uint32_t *scratch;  // side bitmasks of CTA-owned nodes (TASK_CLSW / TASK_REG)
+  int32_t node_base_next;
+};
 
 // ---- roots ----------------------------------------------------------------------------------
 __global__ void k_init_samples(int64_t n, int32_t B, int32_t *idx, const int32_t *y_cls, int32_t *yc,
@@ -138,168 +163,81 @@ __global__ void k_init_roots(P p, int32_t B, const uint64_t *tree_keys, const in
     for (int c = 0; c < p.C; c++) p.cur.hist[(int64_t)t * p.C + c] = root_hist[c];
   if (!p.replay) {
     for (int w = 0; w < p.W; w++) {
-      uint32_t m = 0;
       int lo = w * 32;
-      if (lo + 32 > p.d) m = (p.d - lo >= 32) ? 0u : (p.d <= lo ? 0xffffffffu : (0xffffffffu << (p.d - lo)));
+      uint32_t m = (p.d - lo >= 32) ? 0u : (0xffffffffu << (p.d - lo));  // padding bits count as taken
       p.cur.mask[(int64_t)t * p.W + w] = m;
     }
   }
+  p.q_cur[p.n <= NW_MAX ? 0 : 1][t] = t;
 }
 
-// ---- classify: the reference's stop rules + node totals ---------------------------------------
-__device__ __forceinline__ void search_init(const P &p, int i) {
-  p.s.flag[i] = FLAG_SEARCH;
-  p.s.visited[i] = 0;
-  p.s.dc[i] = 0;
-  p.s.cand_begin[i] = 0;
-  p.s.cand_cnt[i] = 0;
-  p.s.best_feature[i] = -1;
-  p.s.best_nleft[i] = 0;
-  p.s.best_mil[i] = 0;
-  p.s.best_score[i] = -INFINITY;
-  p.s.best_cut[i] = NAN;
-  p.s.split_slot[i] = -1;
+// ---- team helpers ---------------------------------------------------------------------------
+template <int TEAM>
+__device__ __forceinline__ void team_sync() {
+  if (TEAM == 32)
+    __syncwarp();
+  else
+    __syncthreads();
 }
 
-// TASK_CLS: stop rules of pkg:993-994 from the node's integer class histogram; Gini total with the
-// reference's repeated `+= 1/s` distribution (pkg:905-911, 1160-1180).
-__global__ void k_classify_cls(P p, int32_t F) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= F) return;
-  const int32_t *h = p.cur.hist + (int64_t)i * p.C;
-  int32_t n = p.cur.end[i] - p.cur.begin[i];
-  bool pure = false;
-  for (int c = 0; c < p.C; c++) pure |= (h[c] == n);
-  p.s.split_slot[i] = -1;
-  p.s.cand_cnt[i] = 0;
-  p.s.best_feature[i] = -1;
-  if (p.n_table < p.n_min || p.cur.depth[i] >= p.max_depth || pure) {
-    p.s.flag[i] = FLAG_LEAF;
-    return;
+// min / max / any over the team; result valid in every thread
+template <int TEAM>
+__device__ __forceinline__ void team_minmax(double &mn, double &mx, int &flag, double *redd, int32_t *redi) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double omn = __shfl_xor_sync(0xffffffffu, mn, o);
+    double omx = __shfl_xor_sync(0xffffffffu, mx, o);
+    if (omn < mn) mn = omn;
+    if (omx > mx) mx = omx;
   }
-  search_init(p, i);
-  p.s.nconst[i] = 0;
-  if (!p.replay) {
-    int nc = 0;
-    const uint32_t *m = p.cur.mask + (int64_t)i * p.W;
-    for (int w = 0; w < p.W; w++) nc += __popc(m[w]);
-    p.s.nconst[i] = nc - (p.W * 32 - p.d);
-  }
-  double inv = ET_DIV(1.0, (double)n);
-  double s = 0.0;
-  for (int c = 0; c < p.C; c++) {
-    double pc = et_repeat_add(inv, h[c]);
-    s = ET_ADD(s, ET_MUL(pc, pc));
-  }
-  p.s.total[i] = ET_SUB(1.0, s);
-  p.s.nsum[i] = (double)n;
-  stat_add(p, ST_SROWS, (unsigned long long)n);
-}
-
-// TASK_REG: pkg:799-814 (targetIsConstant with !=), leaf mean (mean2, pkg:782), varianceNoSplit
-// (pkg:436-437) -- all sequential in subset order.
-__global__ void k_classify_reg(P p, int32_t F) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= F) return;
-  int32_t b = p.cur.begin[i], e = p.cur.end[i];
-  int32_t n = e - b;
-  const double *y = p.yr_src + (int64_t)p.cur.tree[i] * p.n;
-  double head = y[b];
-  bool uniform = true;
-  double sum = 0.0;
-  for (int32_t j = b; j < e; j++) {
-    double v = y[j];
-    sum = ET_ADD(sum, v);
-    uniform &= !(v != head);
-  }
-  double dn = (double)n;
-  double mean = ET_DIV(sum, dn);
-  p.s.mean[i] = mean;
-  p.s.split_slot[i] = -1;
-  p.s.cand_cnt[i] = 0;
-  p.s.best_feature[i] = -1;
-  if (n < p.n_min || p.cur.depth[i] >= p.max_depth || uniform) {
-    p.s.flag[i] = FLAG_LEAF;
-    return;
-  }
-  search_init(p, i);
-  p.s.nconst[i] = 0;
-  if (!p.replay) {
-    int nc = 0;
-    const uint32_t *m = p.cur.mask + (int64_t)i * p.W;
-    for (int w = 0; w < p.W; w++) nc += __popc(m[w]);
-    p.s.nconst[i] = nc - (p.W * 32 - p.d);
-  }
-  // sampleVariance: two-pass; n == 1 -> 0
-  double var;
-  if (n == 1) {
-    var = 0.0;
-  } else {
-    double q = 0.0;
-    for (int32_t j = b; j < e; j++) {
-      double dl = ET_SUB(y[j], mean);
-      q = ET_ADD(q, ET_MUL(dl, dl));
+  flag = __any_sync(0xffffffffu, flag);
+  if (TEAM > 32) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = TEAM / 32;
+    __syncthreads();  // previous users of the scratch are done
+    if (lane == 0) {
+      redd[w] = mn;
+      redd[32 + w] = mx;
+      redi[w] = flag;
     }
-    var = ET_DIV(q, ET_SUB(dn, 1.0));
+    __syncthreads();
+    double a = lane < nw ? redd[lane] : 1.7976931348623157e308;
+    double b = lane < nw ? redd[32 + lane] : -1.7976931348623157e308;
+    int f = lane < nw ? redi[lane] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double oa = __shfl_xor_sync(0xffffffffu, a, o);
+      double ob = __shfl_xor_sync(0xffffffffu, b, o);
+      if (oa < a) a = oa;
+      if (ob > b) b = ob;
+    }
+    mn = a;
+    mx = b;
+    flag = __any_sync(0xffffffffu, f);
   }
-  p.s.total[i] = ET_DIV(ET_MUL(var, ET_SUB(dn, 1.0)), dn);
-  p.s.nsum[i] = dn;
-  stat_add(p, ST_SROWS, (unsigned long long)n);
 }
 
-// TASK_CLSW: weighted distribution (pkg:913-927) summed in subset order; also the leaf value.
-__global__ void k_classify_clsw(P p, int32_t F) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= F) return;
-  int32_t b = p.cur.begin[i], e = p.cur.end[i];
-  int32_t n = e - b;
-  int64_t base = (int64_t)p.cur.tree[i] * p.n;
-  const int32_t *y = p.yc_src + base;
-  const double *w = p.w_src + base;
-  double *dist = p.s.dist + (int64_t)i * p.C;
-  for (int c = 0; c < p.C; c++) dist[c] = 0.0;
-  double s = 0.0;
-  int32_t head = y[b];
-  bool uniform = true;
-  for (int32_t j = b; j < e; j++) {
-    int32_t cls = y[j];
-    double ww = w[j];
-    dist[cls] = ET_ADD(dist[cls], ww);
-    s = ET_ADD(s, ww);
-    uniform &= (cls == head);
+template <int TEAM>
+__device__ __forceinline__ bool team_all(bool v, int32_t *redi) {
+  bool r = __all_sync(0xffffffffu, v);
+  if (TEAM > 32) {
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) redi[64 + (threadIdx.x >> 5)] = r;
+    __syncthreads();
+    bool a = true;
+    for (int w = 0; w < TEAM / 32; w++) a &= (redi[64 + w] != 0);
+    r = a;
   }
-  double sq = 0.0;
-  for (int c = 0; c < p.C; c++) {
-    double pc = ET_DIV(dist[c], s);
-    dist[c] = pc;
-    sq = ET_ADD(sq, ET_MUL(pc, pc));
-  }
-  p.s.split_slot[i] = -1;
-  p.s.cand_cnt[i] = 0;
-  p.s.best_feature[i] = -1;
-  if (p.n_table < p.n_min || p.cur.depth[i] >= p.max_depth || uniform) {
-    p.s.flag[i] = FLAG_LEAF;
-    return;
-  }
-  search_init(p, i);
-  p.s.nconst[i] = 0;
-  if (!p.replay) {
-    int nc = 0;
-    const uint32_t *m = p.cur.mask + (int64_t)i * p.W;
-    for (int w2 = 0; w2 < p.W; w2++) nc += __popc(m[w2]);
-    p.s.nconst[i] = nc - (p.W * 32 - p.d);
-  }
-  p.s.total[i] = ET_SUB(1.0, sq);
-  p.s.nsum[i] = s;  // sampleWeights.sum2 over the subset (pkg:1112): same order, same value
-  stat_add(p, ST_SROWS, (unsigned long long)n);
+  return r;
 }
 
-// ---- Gini score of one candidate from integer histograms (pkg:1101-1158, unweighted) ---------
-// hin[c] = hl[c] (+ hn[c] when NaN rows go left); hout = node hist - hin.
+// ---- exact scores ---------------------------------------------------------------------------
+// giniScore (pkg:1101-1158, unweighted) from integer histograms: hin[c] = hl[c] (+ hn[c] when NaN
+// rows go left); hout = node histogram - hin.
 __device__ double gini_score_int(const int32_t *hnode, const int32_t *hl, const int32_t *hn, bool nan_left, int C,
-                                 int32_t n, double G) {
+                                 int32_t n, double G, int32_t *cin_out) {
   int32_t cin_i = 0;
   for (int c = 0; c < C; c++) cin_i += hl[c] + (nan_left ? hn[c] : 0);
+  *cin_out = cin_i;
   double cin = (double)cin_i, cout = (double)(n - cin_i), N = (double)n;
   double sin_ = 0.0, sout = 0.0;
   for (int c = 0; c < C; c++) {
@@ -313,257 +251,9 @@ __device__ double gini_score_int(const int32_t *hnode, const int32_t *hl, const 
   return ET_SUB(ET_SUB(G, ET_DIV(ET_MUL(gin, cin), N)), ET_DIV(ET_MUL(gout, cout), N));
 }
 
-// ---- free-running feature draw: uniform over features that are neither known-constant nor taken
-__device__ int32_t pick_feature(uint32_t *mask, int32_t d, int32_t W, int32_t avail, uint64_t key, int32_t &dc) {
-  for (int t = 0; t < 6; t++) {
-    uint64_t r = et_draw(key, (uint32_t)dc++);
-    int32_t f = (int32_t)__umul64hi(r, (uint64_t)d);
-    uint32_t bit = 1u << (f & 31);
-    if (!(mask[f >> 5] & bit)) {
-      mask[f >> 5] |= bit;
-      return f;
-    }
-  }
-  uint64_t r = et_draw(key, (uint32_t)dc++);
-  int32_t rank = (int32_t)__umul64hi(r, (uint64_t)avail);
-  for (int w = 0; w < W; w++) {
-    uint32_t z = ~mask[w];
-    int c = __popc(z);
-    if (rank < c) {
-      for (int q = 0; q < rank; q++) z &= z - 1;  // drop the lowest set bits
-      int pos = __ffs(z) - 1;
-      mask[w] |= 1u << pos;
-      return w * 32 + pos;
-    }
-    rank -= c;
-  }
-  return -1;  // unreachable when avail is consistent
-}
-
-// ---- round kernel: consume the previous round's results, then draw what is still needed -------
-// One thread per frontier node.  Implements the loop of pkg:232-292 / 453-505: candidates are
-// consumed in draw order, constants and NaN-scoring features do not count toward k, strict `>`
-// keeps the first best.
-__global__ void k_update_draw(P p, int32_t F, int round) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= F) return;
-  if (p.s.flag[i] != FLAG_SEARCH) return;
-  const int prev = (round & 1) ^ 1, cur = round & 1;
-  const Cand &cp = p.c[prev];
-  const Cand &cc = p.c[cur];
-  const int32_t n = p.cur.end[i] - p.cur.begin[i];
-  int32_t visited = p.s.visited[i], nconst = p.s.nconst[i];
-  const int C = p.C;
-  // consume
-  int32_t cb = p.s.cand_begin[i], ccnt = p.s.cand_cnt[i];
-  if (ccnt > 0) {
-    double best = p.s.best_score[i];
-    const double G = p.s.total[i];
-    unsigned long long n_const = 0, n_scored = 0;
-    for (int j = 0; j < ccnt; j++) {
-      int c = cb + j;
-      uint8_t fl = cp.flags[c];
-      int32_t f = cp.feature[c];
-      if (fl & CF_CONST) {
-        nconst++;
-        n_const++;
-        if (p.replay && ((fl >> 4) & 3) != 1) stat_add(p, ST_MISMATCH, 1);
-        continue;
-      }
-      n_scored++;
-      double s;
-      bool mil = false;
-      if (p.task == TASK_CLS) {
-        const int32_t *hl = cp.hist + (int64_t)c * 2 * C;
-        const int32_t *hn = hl + C;
-        const int32_t *hnode = p.cur.hist + (int64_t)i * C;
-        double sn = gini_score_int(hnode, hl, hn, false, C, n, G);
-        s = sn;
-        if (fl & CF_NAN) {
-          double sl = gini_score_int(hnode, hl, hn, true, C, n, G);
-          mil = !(sl != sl) && (sl > sn || (sn != sn));
-          if (mil) s = sl;
-        }
-      } else {
-        s = cp.score[c];
-        mil = cp.mil[c] != 0;
-      }
-      if (s > best) {
-        best = s;
-        p.s.best_feature[i] = f;
-        p.s.best_cut[i] = cp.cut[c];
-        p.s.best_mil[i] = mil ? 1 : 0;
-        p.s.best_nleft[i] = cp.cnt_lt[c] + (mil ? cp.cnt_nan[c] : 0);
-        if (p.task == TASK_CLS) {
-          const int32_t *hl = cp.hist + (int64_t)c * 2 * C;
-          int32_t *bh = p.s.best_hl + (int64_t)i * C;
-          for (int q = 0; q < C; q++) bh[q] = hl[q] + (mil ? hl[C + q] : 0);
-        }
-      }
-      if (s != s) {
-        nconst++;  // pkg:283-285: joins the inherited "constant" prefix
-        if (p.replay && ((fl >> 4) & 3) != 3) stat_add(p, ST_MISMATCH, 1);
-      } else {
-        if (!p.replay) p.s.scored[(int64_t)i * p.k + visited] = f;
-        visited++;
-        if (p.replay && ((fl >> 4) & 3) != 2) stat_add(p, ST_MISMATCH, 1);
-      }
-    }
-    p.s.best_score[i] = best;
-    stat_add(p, ST_VMM, (unsigned long long)n * (unsigned long long)ccnt);
-    stat_add(p, ST_VSC, (unsigned long long)n * n_scored);
-    stat_add(p, ST_DRAWS, (unsigned long long)ccnt);
-    stat_add(p, ST_CONST, n_const);
-    stat_add(p, ST_SCORED, n_scored);
-  }
-  // decide
-  int32_t need;
-  int64_t tn = p.cur.trace[i];
-  if (p.replay) {
-    need = (round == 0 && tn >= 0) ? p.tr.cand_count[tn] : 0;
-  } else {
-    int32_t avail = p.d - nconst - visited;
-    need = min(p.k - visited, avail);
-  }
-  p.s.visited[i] = visited;
-  p.s.nconst[i] = nconst;
-  if (need <= 0) {
-    p.s.flag[i] = FLAG_DONE;
-    p.s.cand_cnt[i] = 0;
-    return;
-  }
-  int32_t base = atomicAdd(&p.cnt->n_cand[cur], need);
-  p.s.cand_begin[i] = base;
-  p.s.cand_cnt[i] = need;
-  if (p.task != TASK_CLS) {
-    // side bitmasks: [<cut words][NaN words], n rounded up to 32 each
-    unsigned long long words = 2ull * (unsigned long long)((n + 31) / 32);
-    unsigned long long off = atomicAdd(&p.cnt->mask_words, words * (unsigned long long)need);
-    for (int j = 0; j < need; j++) cc.mask_off[base + j] = (int64_t)(off + words * j);
-  }
-  if (p.replay) {
-    int64_t tb = p.tr.cand_begin[tn];
-    for (int j = 0; j < need; j++) {
-      cc.node[base + j] = i;
-      cc.feature[base + j] = p.tr.cand_feature[tb + j];
-      cc.u[base + j] = p.tr.cand_u[tb + j];
-      cc.flags[base + j] = (uint8_t)((p.tr.cand_flag[tb + j] + 1) << 4);
-    }
-  } else {
-    uint32_t *mask = p.cur.mask + (int64_t)i * p.W;
-    const uint64_t key = p.cur.key[i];
-    int32_t dc = p.s.dc[i];
-    int32_t avail = p.d - nconst - visited;
-    for (int j = 0; j < need; j++) {
-      int32_t f = pick_feature(mask, p.d, p.W, avail - j, key, dc);
-      cc.node[base + j] = i;
-      cc.feature[base + j] = f;
-      cc.u[base + j] = et_u01(et_draw(key, (uint32_t)dc++));
-      cc.flags[base + j] = 0;
-    }
-    p.s.dc[i] = dc;
-  }
-}
-
-// ---- item kernel: one warp per candidate (node, feature) --------------------------------------
-// pass 1: min / max / hasMissing over the node's samples (pkg:34-54; NaN ignored by < and >).
-// constant test `max <= min && !hasMissing` (pkg:236); cut = min + (max - min) * u (pkg:240).
-// pass 2 (same warp, the column segment is still in L1/L2): <cut side.
-//   TASK_CLS : integer class histograms of the <cut rows and of the NaN rows
-//   otherwise: side bitmasks for the sequential scorer
-template <int TASK>
-__global__ void __launch_bounds__(256) k_items_warp(P p, int32_t n_cand, int par) {
-  extern __shared__ int32_t sm_hist[];  // [warps][2][C]
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int c = blockIdx.x * (blockDim.x >> 5) + wib;
-  if (c >= n_cand) return;
-  const Cand &cd = p.c[par];
-  const int i = cd.node[c];
-  const int32_t f = cd.feature[c];
-  const int32_t b = p.cur.begin[i], e = p.cur.end[i];
-  const int64_t base = (int64_t)p.cur.tree[i] * p.n;
-  const int32_t *idx = p.idx_src + base;
-  const double *col = p.X + (int64_t)f * p.ld;
-  double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;
-  int has_nan = 0;
-  for (int32_t j = b + lane; j < e; j += 32) {
-    double x = __ldg(col + idx[j]);
-    if (x < mn) mn = x;
-    if (x > mx) mx = x;
-    has_nan |= (x != x);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    double omn = __shfl_xor_sync(0xffffffffu, mn, o);
-    double omx = __shfl_xor_sync(0xffffffffu, mx, o);
-    if (omn < mn) mn = omn;
-    if (omx > mx) mx = omx;
-  }
-  has_nan = __any_sync(0xffffffffu, has_nan);
-  uint8_t fl = cd.flags[c] & 0xf0;
-  if (mx <= mn && !has_nan) {
-    if (lane == 0) cd.flags[c] = fl | CF_CONST;
-    return;
-  }
-  const double cut = ET_ADD(mn, ET_MUL(ET_SUB(mx, mn), cd.u[c]));
-  int32_t cnt_lt = 0, cnt_nan = 0;
-  if (TASK == TASK_CLS) {
-    const int C = p.C;
-    int32_t *hl = sm_hist + wib * 2 * C, *hn = hl + C;
-    for (int q = lane; q < 2 * C; q += 32) hl[q] = 0;
-    __syncwarp();
-    const int32_t *y = p.yc_src + base;
-    for (int32_t j = b + lane; j < e; j += 32) {
-      double x = __ldg(col + idx[j]);
-      int32_t cls = y[j];
-      if (x < cut) {
-        atomicAdd(&hl[cls], 1);
-        cnt_lt++;
-      } else if (x != x) {
-        atomicAdd(&hn[cls], 1);
-        cnt_nan++;
-      }
-    }
-    __syncwarp();
-    int32_t *gh = cd.hist + (int64_t)c * 2 * C;
-    for (int q = lane; q < 2 * C; q += 32) gh[q] = hl[q];
-  } else {
-    uint32_t *mlt = p.sidemask + cd.mask_off[c];
-    uint32_t *mnan = mlt + (e - b + 31) / 32;
-    for (int32_t j0 = b; j0 < e; j0 += 32) {
-      int32_t j = j0 + lane;
-      bool lt = false, isn = false;
-      if (j < e) {
-        double x = __ldg(col + idx[j]);
-        lt = x < cut;
-        isn = x != x;
-      }
-      uint32_t blt = __ballot_sync(0xffffffffu, lt), bnan = __ballot_sync(0xffffffffu, isn);
-      if (lane == 0) {
-        mlt[(j0 - b) >> 5] = blt;
-        mnan[(j0 - b) >> 5] = bnan;
-      }
-      cnt_lt += lt;
-      cnt_nan += isn;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    cnt_lt += __shfl_xor_sync(0xffffffffu, cnt_lt, o);
-    cnt_nan += __shfl_xor_sync(0xffffffffu, cnt_nan, o);
-  }
-  if (lane == 0) {
-    cd.flags[c] = fl | (has_nan ? CF_NAN : 0);
-    cd.cut[c] = cut;
-    cd.cnt_lt[c] = cnt_lt;
-    cd.cnt_nan[c] = cnt_nan;
-  }
-}
-
-// ---- sequential scorers (one thread per candidate) --------------------------------------------
 // computeVarianceReduction (pkg:1196-1218) with saddle's two-pass sampleVariance, in subset order.
 __device__ double var_reduction_seq(const double *y, int32_t n, const uint32_t *mlt, const uint32_t *mnan,
-                                    bool nan_left, double V) {
+                                    bool nan_left, double V, int32_t *nin_out) {
   double sin_ = 0.0, sout = 0.0;
   int32_t nin = 0;
   for (int32_t j = 0; j < n; j++) {
@@ -577,68 +267,43 @@ __device__ double var_reduction_seq(const double *y, int32_t n, const uint32_t *
       sout = ET_ADD(sout, v);
     }
   }
+  *nin_out = nin;
   int32_t nout = n - nin;
   double dnin = (double)nin, dnout = (double)nout, dn = (double)n;
-  double vin, vout;
-  {
-    double min_ = ET_DIV(sin_, dnin), mout = ET_DIV(sout, dnout);
-    double qin = 0.0, qout = 0.0;
-    for (int32_t j = 0; j < n; j++) {
-      uint32_t w = mlt[j >> 5];
-      if (nan_left) w |= mnan[j >> 5];
-      double v = y[j];
-      if ((w >> (j & 31)) & 1u) {
-        double dl = ET_SUB(v, min_);
-        qin = ET_ADD(qin, ET_MUL(dl, dl));
-      } else {
-        double dl = ET_SUB(v, mout);
-        qout = ET_ADD(qout, ET_MUL(dl, dl));
-      }
+  double min_ = ET_DIV(sin_, dnin), mout = ET_DIV(sout, dnout);
+  double qin = 0.0, qout = 0.0;
+  for (int32_t j = 0; j < n; j++) {
+    uint32_t w = mlt[j >> 5];
+    if (nan_left) w |= mnan[j >> 5];
+    double v = y[j];
+    if ((w >> (j & 31)) & 1u) {
+      double dl = ET_SUB(v, min_);
+      qin = ET_ADD(qin, ET_MUL(dl, dl));
+    } else {
+      double dl = ET_SUB(v, mout);
+      qout = ET_ADD(qout, ET_MUL(dl, dl));
     }
-    // sampleVariance: n < 1 -> NaN, n == 1 -> 0 (pkg:1204 short-circuits n == 1 as well)
-    double svin = nin < 1 ? NAN : (nin == 1 ? 0.0 : ET_DIV(qin, ET_SUB(dnin, 1.0)));
-    double svout = nout < 1 ? NAN : (nout == 1 ? 0.0 : ET_DIV(qout, ET_SUB(dnout, 1.0)));
-    vin = (nin == 1) ? 0.0 : ET_DIV(ET_MUL(svin, ET_SUB(dnin, 1.0)), dnin);
-    vout = (nout == 1) ? 0.0 : ET_DIV(ET_MUL(svout, ET_SUB(dnout, 1.0)), dnout);
   }
+  // sampleVariance: n < 1 -> NaN, n == 1 -> 0 (pkg:1204 short-circuits n == 1 as well)
+  double svin = nin < 1 ? NAN : (nin == 1 ? 0.0 : ET_DIV(qin, ET_SUB(dnin, 1.0)));
+  double svout = nout < 1 ? NAN : (nout == 1 ? 0.0 : ET_DIV(qout, ET_SUB(dnout, 1.0)));
+  double vin = (nin == 1) ? 0.0 : ET_DIV(ET_MUL(svin, ET_SUB(dnin, 1.0)), dnin);
+  double vout = (nout == 1) ? 0.0 : ET_DIV(ET_MUL(svout, ET_SUB(dnout, 1.0)), dnout);
   double a = ET_MUL(ET_DIV(dnin, dn), vin);
   double bq = ET_MUL(ET_DIV(dnout, dn), vout);
   return ET_DIV(ET_SUB(ET_SUB(V, a), bq), V);
 }
 
-__global__ void k_score_reg(P p, int32_t n_cand, int par) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_cand) return;
-  const Cand &cd = p.c[par];
-  uint8_t fl = cd.flags[c];
-  if (fl & CF_CONST) return;
-  int i = cd.node[c];
-  int32_t b = p.cur.begin[i], n = p.cur.end[i] - b;
-  const double *y = p.yr_src + (int64_t)p.cur.tree[i] * p.n + b;
-  const uint32_t *mlt = p.sidemask + cd.mask_off[c];
-  const uint32_t *mnan = mlt + (n + 31) / 32;
-  double V = p.s.total[i];
-  double sn = var_reduction_seq(y, n, mlt, mnan, false, V);
-  double s = sn;
-  bool mil = false;
-  if (fl & CF_NAN) {
-    double sl = var_reduction_seq(y, n, mlt, mnan, true, V);
-    mil = !(sl != sl) && (sl > sn || (sn != sn));
-    if (mil) s = sl;
-  }
-  cd.score[c] = s;
-  cd.mil[c] = mil ? 1 : 0;
-}
-
 // weighted giniScore (pkg:1132-1157): sequential weighted class sums in subset order.
 __device__ double gini_score_w_seq(const int32_t *y, const double *w, int32_t n, const uint32_t *mlt,
                                    const uint32_t *mnan, bool nan_left, int C, double G, double N, double *hin,
-                                   double *hout) {
+                                   double *hout, int32_t *nin_out) {
   for (int q = 0; q < C; q++) {
     hin[q] = 0.0;
     hout[q] = 0.0;
   }
   double cin = 0.0, cout = 0.0;
+  int32_t nin = 0;
   for (int32_t j = 0; j < n; j++) {
     uint32_t m = mlt[j >> 5];
     if (nan_left) m |= mnan[j >> 5];
@@ -647,11 +312,13 @@ __device__ double gini_score_w_seq(const int32_t *y, const double *w, int32_t n,
     if ((m >> (j & 31)) & 1u) {
       cin = ET_ADD(cin, ww);
       hin[cls] = ET_ADD(hin[cls], ww);
+      nin++;
     } else {
       cout = ET_ADD(cout, ww);
       hout[cls] = ET_ADD(hout[cls], ww);
     }
   }
+  *nin_out = nin;
   double sin_ = 0.0, sout = 0.0;
   for (int q = 0; q < C; q++) {
     double pi = ET_DIV(hin[q], cin), po = ET_DIV(hout[q], cout);
@@ -662,263 +329,686 @@ __device__ double gini_score_w_seq(const int32_t *y, const double *w, int32_t n,
   return ET_SUB(ET_SUB(G, ET_DIV(ET_MUL(gin, cin), N)), ET_DIV(ET_MUL(gout, cout), N));
 }
 
-__global__ void k_score_clsw(P p, int32_t n_cand, int par) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_cand) return;
-  const Cand &cd = p.c[par];
-  uint8_t fl = cd.flags[c];
-  if (fl & CF_CONST) return;
-  int i = cd.node[c];
-  int32_t b = p.cur.begin[i], n = p.cur.end[i] - b;
-  int64_t base = (int64_t)p.cur.tree[i] * p.n + b;
-  const int32_t *y = p.yc_src + base;
-  const double *w = p.w_src + base;
-  const uint32_t *mlt = p.sidemask + cd.mask_off[c];
-  const uint32_t *mnan = mlt + (n + 31) / 32;
-  double *hin = p.wscratch + (int64_t)c * 2 * p.C, *hout = hin + p.C;
-  double G = p.s.total[i], N = p.s.nsum[i];
-  double sn = gini_score_w_seq(y, w, n, mlt, mnan, false, p.C, G, N, hin, hout);
-  double s = sn;
-  bool mil = false;
-  if (fl & CF_NAN) {
-    double sl = gini_score_w_seq(y, w, n, mlt, mnan, true, p.C, G, N, hin, hout);
-    mil = !(sl != sl) && (sl > sn || (sn != sn));
-    if (mil) s = sl;
+// position of the rank-th clear bit of taken[0..W) (rank < number of clear bits)
+__device__ __forceinline__ int32_t rank_select_clear(const uint32_t *taken, int W, int32_t rank) {
+  for (int w = 0; w < W; w++) {
+    uint32_t z = ~taken[w];
+    int c = __popc(z);
+    if (rank < c) return w * 32 + (int32_t)__fns(z, 0, rank + 1);
+    rank -= c;
   }
-  cd.score[c] = s;
-  cd.mil[c] = mil ? 1 : 0;
+  return -1;
 }
 
-// ---- finalize: write the output node, open the children ---------------------------------------
-__global__ void k_finalize(P p, int32_t F) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= F) return;
-  const int32_t node = p.cur.node[i];
-  const int C = p.C;
-  const int lw = (p.task == TASK_REG) ? 1 : C;
-  const int32_t b = p.cur.begin[i], e = p.cur.end[i], n = e - b;
-  const int32_t bf = p.s.best_feature[i];
-  const bool leaf = (p.s.flag[i] == FLAG_LEAF) || bf < 0;  // pkg:293-296 (visited == 0 || cut NaN) <=> bf < 0
+// ---- the node kernel ------------------------------------------------------------------------
+// One team per open node (TEAM == 32: a warp, several per CTA; else one CTA).  Implements
+// buildTree* (stop rules, pkg:993-994 / 813-814), split* (pkg:232-296 / 453-509: candidates
+// consumed in draw order, constants and NaN scores do not count toward k, strict `>` keeps the
+// first best), the child filters (pkg:1024-1039) and child creation.
+template <int TASK, int TEAM>
+__global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node(P p, int32_t qcount) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr bool WARP = (TEAM == 32);
+  const int tic = WARP ? (threadIdx.x >> 5) : 0;
+  const int q = WARP ? blockIdx.x * WARPS_PER_CTA + tic : blockIdx.x;
+  if (q >= qcount) return;
+  const int tid = WARP ? (threadIdx.x & 31) : threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int wit = WARP ? 0 : (threadIdx.x >> 5);  // warp index inside the team
+  const int C = p.C, NB = p.NB, W = p.W;
+  const Lay L = make_lay(TASK, WARP, C, NB, W, p.replay != 0);
+  unsigned char *sm = smem_raw + (size_t)tic * L.bytes;
+  double *smd = reinterpret_cast<double *>(sm);
+  int32_t *smi = reinterpret_cast<int32_t *>(sm);
+  double *s_u = smd + L.o_u, *s_cut = smd + L.o_cut, *s_score = smd + L.o_score, *s_dist = smd + L.o_dist;
+  double *s_redd = smd + L.o_redd, *s_wh = smd + L.o_wh;
+  int32_t *s_feat = smi + L.o_feat, *s_flags = smi + L.o_flags, *s_nleft = smi + L.o_nleft;
+  int32_t *s_hnode = smi + L.o_hnode, *s_besthl = smi + L.o_besthl, *s_hist = smi + L.o_hist, *s_redi = smi + L.o_redi;
+  uint32_t *s_const = reinterpret_cast<uint32_t *>(smi + L.o_mask), *s_taken = s_const + W;
+  uint32_t *s_bits = reinterpret_cast<uint32_t *>(smi + L.o_bits);
+  int32_t *s_misc = smi + L.o_misc;
+
+  const int i = p.q_cur[WARP ? 0 : 1][q];
+  const int32_t tree = p.cur.tree[i], b = p.cur.begin[i], e = p.cur.end[i], n = e - b;
+  const int32_t node = p.cur.node[i], depth = p.cur.depth[i];
   const int64_t tn = p.cur.trace[i];
-  if (leaf) {
-    p.o.feature[node] = -1;
-    p.o.left[node] = -1;
-    p.o.right[node] = -1;
-    p.o.cut[node] = NAN;
-    p.o.mil[node] = 0;
-    double *lv = p.o.leaf + (int64_t)node * lw;
-    if (p.task == TASK_CLS) {
-      const int32_t *h = p.cur.hist + (int64_t)i * C;
-      double inv = ET_DIV(1.0, (double)n);
-      for (int c = 0; c < C; c++) lv[c] = et_repeat_add(inv, h[c]);
-    } else if (p.task == TASK_CLSW) {
-      const double *ds = p.s.dist + (int64_t)i * C;
-      for (int c = 0; c < C; c++) lv[c] = ds[c];
-    } else {
-      lv[0] = p.s.mean[i];
+  const uint64_t key = p.cur.key[i];
+  const int64_t base = (int64_t)tree * p.n;
+  const int32_t *idx = p.idx_src + base;
+  const int lw = (TASK == TASK_REG) ? 1 : C;
+
+  // ---------------- stop rules + node totals ----------------
+  bool leaf;
+  double total = 0.0, nsum = (double)n, leaf_mean = 0.0;
+  if (TASK == TASK_CLS) {
+    for (int c = tid; c < C; c += TEAM) s_hnode[c] = p.cur.hist[(int64_t)i * C + c];
+    team_sync<TEAM>();
+    bool pure = false;
+    for (int c = 0; c < C; c++) pure |= (s_hnode[c] == n);
+    leaf = (p.n_table < p.n_min) || (depth >= p.max_depth) || pure;  // pkg:993-994
+    if (!leaf) {
+      // giniImpurity with the reference's repeated `+= 1/s` distribution (pkg:905-911, 1160-1180)
+      const double inv = ET_DIV(1.0, (double)n);
+      for (int c = tid; c < C; c += TEAM) s_dist[c] = et_repeat_add(inv, s_hnode[c]);
+      team_sync<TEAM>();
+      double s = 0.0;
+      for (int c = 0; c < C; c++) s = ET_ADD(s, ET_MUL(s_dist[c], s_dist[c]));
+      total = ET_SUB(1.0, s);
     }
-    if (p.replay && tn >= 0 && p.tr.left[tn] >= 0) stat_add(p, ST_MISMATCH, 1);
+  } else if (TASK == TASK_REG) {
+    const double *y = p.yr_src + base;
+    const double head = y[b];
+    bool uni = true;
+    for (int32_t j = b + tid; j < e; j += TEAM) uni &= !(y[j] != head);
+    uni = team_all<TEAM>(uni, s_redi);
+    leaf = (n < p.n_min) || (depth >= p.max_depth) || uni;  // pkg:813-814
+    // mean2 (pkg:782) and varianceNoSplit (pkg:436-437), sequential in subset order
+    if (tid == 0) {
+      double sum = 0.0;
+      for (int32_t j = b; j < e; j++) sum = ET_ADD(sum, y[j]);
+      const double dn = (double)n;
+      const double mean = ET_DIV(sum, dn);
+      double V = 0.0;
+      if (!leaf) {
+        double var = 0.0;
+        if (n > 1) {
+          double qq = 0.0;
+          for (int32_t j = b; j < e; j++) {
+            double dl = ET_SUB(y[j], mean);
+            qq = ET_ADD(qq, ET_MUL(dl, dl));
+          }
+          var = ET_DIV(qq, ET_SUB(dn, 1.0));
+        }
+        V = ET_DIV(ET_MUL(var, ET_SUB(dn, 1.0)), dn);
+      }
+      s_score[0] = mean;
+      s_score[NB] = V;
+    }
+    team_sync<TEAM>();
+    leaf_mean = s_score[0];
+    total = s_score[NB];
+    team_sync<TEAM>();
+  } else {
+    const int32_t *y = p.yc_src + base;
+    const double *w = p.w_src + base;
+    const int32_t head = y[b];
+    bool uni = true;
+    for (int32_t j = b + tid; j < e; j += TEAM) uni &= (y[j] == head);
+    uni = team_all<TEAM>(uni, s_redi);
+    leaf = (p.n_table < p.n_min) || (depth >= p.max_depth) || uni;
+    // weighted distribution (pkg:913-927): sequential in subset order; also the leaf value
+    if (tid == 0) {
+      for (int c = 0; c < C; c++) s_dist[c] = 0.0;
+      double s = 0.0;
+      for (int32_t j = b; j < e; j++) {
+        const double ww = w[j];
+        const int32_t cls = y[j];
+        s_dist[cls] = ET_ADD(s_dist[cls], ww);
+        s = ET_ADD(s, ww);
+      }
+      double sq = 0.0;
+      for (int c = 0; c < C; c++) {
+        const double pc = ET_DIV(s_dist[c], s);
+        s_dist[c] = pc;
+        sq = ET_ADD(sq, ET_MUL(pc, pc));
+      }
+      s_score[0] = ET_SUB(1.0, sq);
+      s_score[NB] = s;  // sampleWeights.sum2 over the subset (pkg:1112): same order, same value
+    }
+    team_sync<TEAM>();
+    total = s_score[0];
+    nsum = s_score[NB];
+    team_sync<TEAM>();
+  }
+
+  // ---------------- split search ----------------
+  int32_t visited = 0, nconst = 0, best_feature = -1, best_nleft = 0, best_mil = 0;
+  double best_score = -INFINITY, best_cut = NAN;
+  unsigned long long st_draws = 0, st_const = 0, st_scored = 0, st_mismatch = 0;
+  if (!leaf) {
+    int32_t dc = 0, tpos = 0;
+    int64_t tb = 0;
+    int32_t tcnt = 0;
+    if (p.replay) {
+      if (tn >= 0) {
+        tb = p.tr.cand_begin[tn];
+        tcnt = p.tr.cand_count[tn];
+      }
+    } else {
+      for (int w = tid; w < W; w += TEAM) {
+        const uint32_t m = p.cur.mask[(int64_t)i * W + w];
+        s_const[w] = m;
+        s_taken[w] = m;
+      }
+      team_sync<TEAM>();
+      int nc = 0;
+      for (int w = 0; w < W; w++) nc += __popc(s_const[w]);
+      nconst = nc - (W * 32 - p.d);
+    }
+    uint32_t *g_bits = nullptr;  // CTA teams keep side bitmasks in global scratch
+    const int words = (n + 31) / 32;
+    if (TASK != TASK_CLS && !WARP) {
+      if (tid == 0) {
+        unsigned long long off =
+            atomicAdd(&p.cnt->scratch_words, (unsigned long long)NB * 2ull * (unsigned long long)words);
+        s_misc[0] = (int32_t)(off & 0xffffffffull);
+        s_misc[1] = (int32_t)(off >> 32);
+      }
+      team_sync<TEAM>();
+      unsigned long long off = ((unsigned long long)(uint32_t)s_misc[1] << 32) | (uint32_t)s_misc[0];
+      g_bits = p.scratch + off;
+    }
+    for (;;) {
+      int32_t nb;
+      const int32_t avail = p.d - nconst - visited;
+      if (p.replay)
+        nb = min(NB, tcnt - tpos);
+      else
+        nb = min(NB, min(p.k - visited, avail));
+      if (nb <= 0) break;
+      // ---- draw a batch of candidates (one lane per candidate)
+      if (wit == 0) {
+        if (p.replay) {
+          if (lane < nb) {
+            s_feat[lane] = p.tr.cand_feature[tb + tpos + lane];
+            s_u[lane] = p.tr.cand_u[tb + tpos + lane];
+            s_flags[lane] = (p.tr.cand_flag[tb + tpos + lane] + 1) << 4;
+          }
+        } else {
+          // uniform over the features that are neither known-constant nor taken; a lane whose pick
+          // collides with a lower lane's pick sits this batch out (= sequential rejection sampling)
+          int32_t f = -1 - lane;
+          if (lane < nb) {
+            const uint64_t r = et_draw(key, (uint32_t)(dc + 2 * lane));
+            f = rank_select_clear(s_taken, W, (int32_t)__umul64hi(r, (uint64_t)avail));
+          }
+          const uint32_t same = __match_any_sync(0xffffffffu, f);
+          const bool keep = (lane < nb) && (lane == __ffs(same) - 1);
+          if (lane < nb) {
+            s_feat[lane] = keep ? f : -1;
+            s_u[lane] = et_u01(et_draw(key, (uint32_t)(dc + 2 * lane + 1)));
+            s_flags[lane] = 0;
+          }
+          __syncwarp();
+          if (keep) atomicOr(&s_taken[f >> 5], 1u << (f & 31));
+        }
+      }
+      if (p.replay)
+        tpos += nb;
+      else
+        dc += 2 * NB;
+      if (TASK == TASK_CLS)
+        for (int t = tid; t < nb * L.hs; t += TEAM) s_hist[t] = 0;
+      team_sync<TEAM>();
+      // ---- phase 1: the whole team on the samples of one candidate at a time
+      for (int c = 0; c < nb; c++) {
+        const int32_t f = s_feat[c];
+        if (f < 0) continue;
+        const double *col = p.X + (int64_t)f * p.ld;
+        double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;  // pkg:35-36
+        int has_nan = 0;
+        for (int32_t j = b + tid; j < e; j += TEAM) {
+          const double x = __ldg(col + idx[j]);
+          if (x < mn) mn = x;
+          if (x > mx) mx = x;
+          has_nan |= (x != x);
+        }
+        team_minmax<TEAM>(mn, mx, has_nan, s_redd, s_redi);
+        if (mx <= mn && !has_nan) {  // pkg:236
+          if (tid == 0) s_flags[c] |= CF_CONST;
+          continue;
+        }
+        const double cut = ET_ADD(mn, ET_MUL(ET_SUB(mx, mn), s_u[c]));  // nextDouble(min, max), pkg:240
+        if (tid == 0) {
+          s_cut[c] = cut;
+          if (has_nan) s_flags[c] |= CF_NAN;
+        }
+        if (TASK == TASK_CLS) {
+          const int32_t *y = p.yc_src + base;
+          int32_t *hl = s_hist + c * L.hs, *hn = hl + C;
+          if (C <= 32) {
+            // lane == class: warp-aggregated counts
+            int32_t al = 0, an = 0;
+            for (int32_t j0 = b + wit * 32; j0 < e; j0 += TEAM) {
+              const int32_t j = j0 + lane;
+              bool lt = false, isn = false;
+              int32_t cls = -1;
+              if (j < e) {
+                const double x = __ldg(col + idx[j]);
+                cls = y[j];
+                lt = x < cut;
+                isn = x != x;
+              }
+              for (int cc = 0; cc < C; cc++) {
+                const uint32_t bl = __ballot_sync(0xffffffffu, lt && cls == cc);
+                if (lane == cc) al += __popc(bl);
+              }
+              if (has_nan) {
+                for (int cc = 0; cc < C; cc++) {
+                  const uint32_t bn = __ballot_sync(0xffffffffu, isn && cls == cc);
+                  if (lane == cc) an += __popc(bn);
+                }
+              }
+            }
+            if (lane < C) {
+              if (WARP) {
+                hl[lane] = al;
+                hn[lane] = an;
+              } else {
+                if (al) atomicAdd(&hl[lane], al);
+                if (an) atomicAdd(&hn[lane], an);
+              }
+            }
+          } else {
+            for (int32_t j = b + tid; j < e; j += TEAM) {
+              const double x = __ldg(col + idx[j]);
+              if (x < cut)
+                atomicAdd(&hl[y[j]], 1);
+              else if (x != x)
+                atomicAdd(&hn[y[j]], 1);
+            }
+          }
+        } else {
+          uint32_t *mlt = WARP ? (s_bits + (size_t)c * 2 * BITS_W) : (g_bits + (size_t)c * 2 * words);
+          uint32_t *mnan = mlt + (WARP ? BITS_W : words);
+          for (int32_t j0 = b + wit * 32; j0 < e; j0 += TEAM) {
+            const int32_t j = j0 + lane;
+            bool lt = false, isn = false;
+            if (j < e) {
+              const double x = __ldg(col + idx[j]);
+              lt = x < cut;
+              isn = x != x;
+            }
+            const uint32_t blt = __ballot_sync(0xffffffffu, lt), bnan = __ballot_sync(0xffffffffu, isn);
+            if (lane == 0) {
+              mlt[(j0 - b) >> 5] = blt;
+              mnan[(j0 - b) >> 5] = bnan;
+            }
+          }
+        }
+      }
+      team_sync<TEAM>();
+      // ---- phase 2: one thread per candidate evaluates the reference's score expression exactly
+      if (tid < nb && s_feat[tid] >= 0 && !(s_flags[tid] & CF_CONST)) {
+        const int c = tid;
+        const bool has_nan = (s_flags[c] & CF_NAN) != 0;
+        double sn, sl = NAN;
+        int32_t nin_n = 0, nin_l = 0;
+        if (TASK == TASK_CLS) {
+          const int32_t *hl = s_hist + c * L.hs, *hn = hl + C;
+          sn = gini_score_int(s_hnode, hl, hn, false, C, n, total, &nin_n);
+          if (has_nan) sl = gini_score_int(s_hnode, hl, hn, true, C, n, total, &nin_l);
+        } else {
+          const uint32_t *mlt = WARP ? (s_bits + (size_t)c * 2 * BITS_W) : (g_bits + (size_t)c * 2 * words);
+          const uint32_t *mnan = mlt + (WARP ? BITS_W : words);
+          if (TASK == TASK_REG) {
+            const double *y = p.yr_src + base + b;
+            sn = var_reduction_seq(y, n, mlt, mnan, false, total, &nin_n);
+            if (has_nan) sl = var_reduction_seq(y, n, mlt, mnan, true, total, &nin_l);
+          } else {
+            const int32_t *y = p.yc_src + base + b;
+            const double *w = p.w_src + base + b;
+            double *hin = s_wh + (size_t)c * 2 * C, *hout = hin + C;
+            sn = gini_score_w_seq(y, w, n, mlt, mnan, false, C, total, nsum, hin, hout, &nin_n);
+            if (has_nan) sl = gini_score_w_seq(y, w, n, mlt, mnan, true, C, total, nsum, hin, hout, &nin_l);
+          }
+        }
+        // pkg:272-275
+        const bool mil = !(sl != sl) && (sl > sn || (sn != sn));
+        s_score[c] = mil ? sl : sn;
+        s_nleft[c] = mil ? nin_l : nin_n;
+        if (mil) s_flags[c] |= CF_MIL;
+      }
+      team_sync<TEAM>();
+      // ---- consume the batch in draw order (every warp computes the same result; warp 0 of the
+      //      team applies the side effects)
+      {
+        const bool act = lane < nb && s_feat[lane] >= 0;
+        const int32_t fl = act ? s_flags[lane] : 0;
+        const bool is_const = act && (fl & CF_CONST);
+        const double s = (act && !is_const) ? s_score[lane] : NAN;
+        const bool is_nan = act && !is_const && (s != s);
+        const bool counted = act && !is_const && !is_nan;
+        const uint32_t m_act = __ballot_sync(0xffffffffu, act);
+        const uint32_t m_const = __ballot_sync(0xffffffffu, is_const);
+        const uint32_t m_nan = __ballot_sync(0xffffffffu, is_nan);
+        const uint32_t m_cnt = __ballot_sync(0xffffffffu, counted);
+        if (p.replay) {
+          const int exp = (fl >> 4) & 3;
+          const bool bad = act && ((is_const && exp != 1) || (is_nan && exp != 3) || (counted && exp != 2));
+          st_mismatch += __popc(__ballot_sync(0xffffffffu, bad));
+        }
+        // first maximum in lane order among the counted candidates (NaN never wins, pkg:277)
+        double bs = counted ? s : -INFINITY;
+        int bl = counted ? lane : 64;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+          const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+          if (os > bs || (os == bs && ol < bl)) {
+            bs = os;
+            bl = ol;
+          }
+        }
+        if (bl < 32 && bs > best_score) {
+          best_score = bs;
+          best_feature = s_feat[bl];
+          best_cut = s_cut[bl];
+          best_mil = (s_flags[bl] & CF_MIL) ? 1 : 0;
+          best_nleft = s_nleft[bl];
+          if (TASK == TASK_CLS && wit == 0) {
+            const int32_t *hl = s_hist + bl * L.hs;
+            for (int c = lane; c < C; c += 32) s_besthl[c] = hl[c] + (best_mil ? hl[C + c] : 0);
+          }
+        }
+        if (!p.replay && wit == 0 && (is_const || is_nan)) {
+          const int32_t f = s_feat[lane];
+          atomicOr(&s_const[f >> 5], 1u << (f & 31));  // pkg:236-238, 283-285: inherited by the children
+        }
+        visited += __popc(m_cnt);
+        nconst += __popc(m_const) + __popc(m_nan);
+        st_draws += __popc(m_act);
+        st_const += __popc(m_const);
+        st_scored += __popc(m_cnt) + __popc(m_nan);
+      }
+      team_sync<TEAM>();
+    }
+  }
+
+  // ---------------- finalize ----------------
+  const bool make_leaf = leaf || best_feature < 0;  // pkg:293-296: visited == 0 || cut.isNaN  <=>  no best
+  if (tid == 0) {
+    if (!leaf) {
+      atomicAdd(&p.cnt->st[ST_SROWS], (unsigned long long)n);
+      atomicAdd(&p.cnt->st[ST_VMM], (unsigned long long)n * st_draws);
+      atomicAdd(&p.cnt->st[ST_VSC], (unsigned long long)n * st_scored);
+      atomicAdd(&p.cnt->st[ST_DRAWS], st_draws);
+      atomicAdd(&p.cnt->st[ST_CONST], st_const);
+      atomicAdd(&p.cnt->st[ST_SCORED], st_scored);
+    }
+    if (p.replay) {
+      const bool trace_split = tn >= 0 && p.tr.left[tn] >= 0;
+      if (trace_split == make_leaf) st_mismatch++;
+      if (st_mismatch) atomicAdd(&p.cnt->st[ST_MISMATCH], st_mismatch);
+    }
+  }
+  if (make_leaf) {
+    if (tid == 0) {
+      s_misc[2] = atomicAdd(&p.cnt->n_leaves, 1);
+      p.o.feat[node] = -1;
+      p.o.child[node] = s_misc[2];
+      p.o.cut[node] = NAN;
+      p.o.tree[node] = tree;
+    }
+    team_sync<TEAM>();
+    double *lv = p.o.leaf_vals + (int64_t)s_misc[2] * lw;
+    if (TASK == TASK_CLS) {
+      const double inv = ET_DIV(1.0, (double)n);
+      for (int c = tid; c < C; c += TEAM) lv[c] = et_repeat_add(inv, s_hnode[c]);  // pkg:960-964
+    } else if (TASK == TASK_CLSW) {
+      for (int c = tid; c < C; c += TEAM) lv[c] = s_dist[c];
+    } else {
+      if (tid == 0) lv[0] = leaf_mean;
+    }
     return;
   }
-  const int32_t nl = p.s.best_nleft[i];
-  const int32_t slot = atomicAdd(&p.cnt->next_f, 2);
-  p.s.split_slot[i] = slot;
-  const int32_t cl = p.node_base_next + slot, cr = cl + 1;
-  p.o.feature[node] = bf;
-  p.o.cut[node] = p.s.best_cut[i];
-  p.o.mil[node] = p.s.best_mil[i];
-  p.o.left[node] = cl;
-  p.o.right[node] = cr;
-  double *lv = p.o.leaf + (int64_t)node * lw;
-  for (int c = 0; c < lw; c++) lv[c] = 0.0;
-  const int32_t t = p.cur.tree[i], dep = p.cur.depth[i];
-  p.nxt.tree[slot] = t;
-  p.nxt.tree[slot + 1] = t;
-  p.nxt.begin[slot] = b;
-  p.nxt.end[slot] = b + nl;
-  p.nxt.begin[slot + 1] = b + nl;
-  p.nxt.end[slot + 1] = e;
-  p.nxt.node[slot] = cl;
-  p.nxt.node[slot + 1] = cr;
-  p.nxt.depth[slot] = dep + 1;
-  p.nxt.depth[slot + 1] = (p.task == TASK_REG) ? dep : dep + 1;  // pkg:884 (sic) vs pkg:1071
-  const uint64_t key = p.cur.key[i];
-  p.nxt.key[slot] = et_child_key(key, 0);
-  p.nxt.key[slot + 1] = et_child_key(key, 1);
-  int64_t tl = -1, trr = -1;
-  if (p.replay) {
-    if (tn >= 0 && p.tr.left[tn] >= 0) {
-      // trace child ids are tree-local pre-order ids; tn - (its own local id) is not stored, so
-      // the host rewrote left/right to absolute node indices before upload
-      tl = p.tr.left[tn];
-      trr = p.tr.right[tn];
-    } else {
-      stat_add(p, ST_MISMATCH, 1);
+  if (tid == 0) {
+    const int32_t slot = atomicAdd(&p.cnt->next_f, 2);
+    s_misc[2] = slot;
+    const int32_t cl = p.node_base_next + slot;
+    p.o.feat[node] = best_feature | (best_mil ? ET_MIL_BIT : 0);
+    p.o.child[node] = cl;
+    p.o.cut[node] = best_cut;
+    p.o.tree[node] = tree;
+    const int32_t nl = best_nleft;
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+      const int32_t s2 = slot + side;
+      p.nxt.tree[s2] = tree;
+      p.nxt.begin[s2] = side ? b + nl : b;
+      p.nxt.end[s2] = side ? e : b + nl;
+      p.nxt.node[s2] = cl + side;
+      // pkg:870 / 884 (sic): the regression right child keeps currentDepth; pkg:1055,1071: +1 both
+      p.nxt.depth[s2] = (TASK == TASK_REG && side) ? depth : depth + 1;
+      p.nxt.key[s2] = et_child_key(key, side);
+      int64_t tc = -1;
+      if (p.replay && tn >= 0) tc = side ? p.tr.right[tn] : p.tr.left[tn];
+      p.nxt.trace[s2] = tc;
+      const int32_t cn = side ? (n - nl) : nl;
+      const int qc = cn <= NW_MAX ? 0 : 1;
+      p.q_nxt[qc][atomicAdd(&p.cnt->q_count[qc], 1)] = s2;
     }
+    atomicAdd(&p.cnt->st[ST_PROWS], (unsigned long long)n);
   }
-  p.nxt.trace[slot] = tl;
-  p.nxt.trace[slot + 1] = trr;
-  if (p.task == TASK_CLS) {
-    const int32_t *h = p.cur.hist + (int64_t)i * C;
-    const int32_t *bh = p.s.best_hl + (int64_t)i * C;
+  team_sync<TEAM>();
+  const int32_t slot = s_misc[2];
+  if (TASK == TASK_CLS) {
     int32_t *hl = p.nxt.hist + (int64_t)slot * C, *hr = hl + C;
-    for (int c = 0; c < C; c++) {
-      hl[c] = bh[c];
-      hr[c] = h[c] - bh[c];
+    for (int c = tid; c < C; c += TEAM) {
+      hl[c] = s_besthl[c];
+      hr[c] = s_hnode[c] - s_besthl[c];
     }
   }
   if (!p.replay) {
-    // children inherit the known-constant set; features merely scored here are released
-    uint32_t *m = p.cur.mask + (int64_t)i * p.W;
-    const int32_t *sc = p.s.scored + (int64_t)i * p.k;
-    const int32_t vis = p.s.visited[i];
-    for (int q = 0; q < vis; q++) m[sc[q] >> 5] &= ~(1u << (sc[q] & 31));
-    uint32_t *ml = p.nxt.mask + (int64_t)slot * p.W, *mr = ml + p.W;
-    for (int w = 0; w < p.W; w++) {
-      uint32_t v = m[w];
+    uint32_t *ml = p.nxt.mask + (int64_t)slot * W, *mr = ml + W;
+    for (int w = tid; w < W; w += TEAM) {
+      const uint32_t v = s_const[w];
       ml[w] = v;
       mr[w] = v;
     }
   }
-  stat_add(p, ST_PROWS, (unsigned long long)n);
-}
-
-// ---- stable partition (pkg:1024-1039 / 841-856): one warp per split node ----------------------
-__global__ void __launch_bounds__(256) k_partition_warp(P p, int32_t F) {
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= F) return;
-  if (p.s.split_slot[i] < 0) return;
-  const int32_t b = p.cur.begin[i], e = p.cur.end[i];
-  const int64_t base = (int64_t)p.cur.tree[i] * p.n;
-  const double *col = p.X + (int64_t)p.s.best_feature[i] * p.ld;
-  const double cut = p.s.best_cut[i];
-  const bool mil = p.s.best_mil[i] != 0;
-  int32_t lpos = b, rpos = b + p.s.best_nleft[i];
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  for (int32_t j0 = b; j0 < e; j0 += 32) {
-    const int32_t j = j0 + lane;
-    const bool valid = j < e;
-    int32_t r = 0;
-    bool left = false;
-    if (valid) {
-      r = p.idx_src[base + j];
-      double x = __ldg(col + r);
-      left = (x < cut) || (mil && (x != x));
-    }
-    const uint32_t bv = __ballot_sync(0xffffffffu, valid);
-    const uint32_t bl = __ballot_sync(0xffffffffu, left);
-    const uint32_t br = bv & ~bl;
-    if (valid) {
-      const int32_t dst = left ? lpos + __popc(bl & lt_mask) : rpos + __popc(br & lt_mask);
-      p.idx_dst[base + dst] = r;
-      if (p.task == TASK_REG) {
-        p.yr_dst[base + dst] = p.yr_src[base + j];
-      } else {
-        p.yc_dst[base + dst] = p.yc_src[base + j];
-        if (p.task == TASK_CLSW) p.w_dst[base + dst] = p.w_src[base + j];
+  // ---- stable partition of the node's segment (pkg:1024-1039)
+  {
+    const double *col = p.X + (int64_t)best_feature * p.ld;
+    const bool mil = best_mil != 0;
+    int32_t lpos = b, rpos = b + best_nleft;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int32_t j0 = b; j0 < e; j0 += TEAM) {
+      const int32_t j = j0 + tid;
+      const bool valid = j < e;
+      int32_t r = 0;
+      bool left = false;
+      if (valid) {
+        r = idx[j];
+        const double x = __ldg(col + r);
+        left = (x < best_cut) || (mil && (x != x));
       }
+      const uint32_t bv = __ballot_sync(0xffffffffu, valid);
+      const uint32_t bl = __ballot_sync(0xffffffffu, left);
+      const uint32_t br = bv & ~bl;
+      int32_t lbase = lpos, rbase = rpos, ltot = __popc(bl), rtot = __popc(br);
+      if (!WARP) {
+        __syncthreads();
+        if (lane == 0) {
+          s_redi[wit] = ltot;
+          s_redi[32 + wit] = rtot;
+        }
+        __syncthreads();
+        ltot = 0;
+        rtot = 0;
+        for (int w = 0; w < TEAM / 32; w++) {
+          const int32_t a = s_redi[w], c2 = s_redi[32 + w];
+          if (w < wit) {
+            lbase += a;
+            rbase += c2;
+          }
+          ltot += a;
+          rtot += c2;
+        }
+      }
+      if (valid) {
+        const int32_t dst = left ? lbase + __popc(bl & lt_mask) : rbase + __popc(br & lt_mask);
+        p.idx_dst[base + dst] = r;
+        if (TASK == TASK_REG) {
+          p.yr_dst[base + dst] = p.yr_src[base + j];
+        } else {
+          p.yc_dst[base + dst] = p.yc_src[base + j];
+          if (TASK == TASK_CLSW) p.w_dst[base + dst] = p.w_src[base + j];
+        }
+      }
+      lpos += ltot;
+      rpos += rtot;
     }
-    lpos += __popc(bl);
-    rpos += __popc(br);
   }
 }
 
-// ---- host orchestration -----------------------------------------------------------------------
-struct LevelBufs {
+// ---- pool (creation order) -> per-tree pre-order ----------------------------------------------
+__global__ void k_subtree_sizes(Pool o, int32_t lo, int32_t hi, int32_t *size, int32_t *nleaf) {
+  int v = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= hi) return;
+  if (o.feat[v] < 0) {
+    size[v] = 1;
+    nleaf[v] = 1;
+  } else {
+    int c = o.child[v];
+    size[v] = 1 + size[c] + size[c + 1];
+    nleaf[v] = nleaf[c] + nleaf[c + 1];
+  }
+}
+
+// one thread: exclusive scan over the batch's roots -> per-tree node / leaf offsets (forest-wide)
+__global__ void k_root_offsets(int32_t B, const int32_t *size, const int32_t *nleaf, int64_t node_base,
+                               int64_t leaf_base, int64_t *tree_off, int64_t *leaf_off, int32_t *pos, int32_t *lpos) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int64_t a = node_base, l = leaf_base;
+    for (int t = 0; t < B; t++) {
+      tree_off[t] = a;
+      leaf_off[t] = l;
+      a += size[t];
+      l += nleaf[t];
+      pos[t] = 0;
+      lpos[t] = 0;
+    }
+    tree_off[B] = a;
+    leaf_off[B] = l;
+  }
+}
+
+__global__ void k_assign_pos(Pool o, int32_t lo, int32_t hi, const int32_t *size, const int32_t *nleaf, int32_t *pos,
+                             int32_t *lpos) {
+  int v = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= hi) return;
+  if (o.feat[v] >= 0) {
+    int c = o.child[v];
+    pos[c] = pos[v] + 1;
+    lpos[c] = lpos[v];
+    pos[c + 1] = pos[v] + 1 + size[c];
+    lpos[c + 1] = lpos[v] + nleaf[c];
+  }
+}
+
+__global__ void k_scatter(Pool o, int32_t n_nodes, int lw, const int32_t *pos, const int32_t *lpos,
+                          const int64_t *tree_off, const int64_t *leaf_off, int64_t node_base, int64_t leaf_base,
+                          PNode *nodes, double *leaves) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_nodes) return;
+  const int t = o.tree[v];
+  PNode pn;
+  const int64_t g = tree_off[t] - node_base + pos[v];
+  if (o.feat[v] >= 0) {
+    pn.cut = o.cut[v];
+    pn.feat = o.feat[v];
+    pn.right_or_leaf = pos[o.child[v] + 1];
+  } else {
+    const int64_t gl = leaf_off[t] + lpos[v];
+    pn.cut = NAN;
+    pn.feat = -1;
+    pn.right_or_leaf = (int32_t)gl;
+    const double *src = o.leaf_vals + (int64_t)o.child[v] * lw;
+    double *dst = leaves + (gl - leaf_base) * lw;
+    for (int c = 0; c < lw; c++) dst[c] = src[c];
+  }
+  nodes[g] = pn;
+}
+
+template <typename T>
+static T *upload_tmp(const T *h, size_t n, cudaStream_t st) {
+  T *d = nullptr;
+  if (cudaMalloc((void **)&d, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) {
+    cudaGetLastError();
+    ET_FAIL(ET_ENOMEM, "device allocation failed");
+  }
+  if (n) cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, st);
+  return d;
+}
+
+struct FrontierBufs {
   DevBuf<int32_t> tree, begin, end, node, depth, hist;
   DevBuf<int64_t> trace;
   DevBuf<uint64_t> key;
   DevBuf<uint32_t> mask;
   void ensure(size_t F, int C, int W, bool need_hist, bool need_mask) {
-    tree.ensure(F);
-    begin.ensure(F);
-    end.ensure(F);
-    node.ensure(F);
-    depth.ensure(F);
-    trace.ensure(F);
-    key.ensure(F);
-    if (need_hist) hist.ensure(F * (size_t)C);
-    if (need_mask) mask.ensure(F * (size_t)W);
+    tree.ensure(F, 1.5);
+    begin.ensure(F, 1.5);
+    end.ensure(F, 1.5);
+    node.ensure(F, 1.5);
+    depth.ensure(F, 1.5);
+    trace.ensure(F, 1.5);
+    key.ensure(F, 1.5);
+    if (need_hist) hist.ensure(F * (size_t)C, 1.5);
+    if (need_mask) mask.ensure(F * (size_t)W, 1.5);
   }
-  Level view() { return Level{tree.p, begin.p, end.p, node.p, depth.p, trace.p, key.p, hist.p, mask.p}; }
+  Frontier view() { return Frontier{tree.p, begin.p, end.p, node.p, depth.p, trace.p, key.p, hist.p, mask.p}; }
 };
 
-struct SearchBufs {
-  DevBuf<uint8_t> flag, best_mil;
-  DevBuf<int32_t> visited, nconst, dc, cand_begin, cand_cnt, best_feature, best_nleft, split_slot, scored, best_hl;
-  DevBuf<double> best_score, best_cut, total, nsum, mean, dist;
-  void ensure(size_t F, int C, int k, int task, bool replay) {
-    flag.ensure(F);
-    best_mil.ensure(F);
-    visited.ensure(F);
-    nconst.ensure(F);
-    dc.ensure(F);
-    cand_begin.ensure(F);
-    cand_cnt.ensure(F);
-    best_feature.ensure(F);
-    best_nleft.ensure(F);
-    split_slot.ensure(F);
-    best_score.ensure(F);
-    best_cut.ensure(F);
-    total.ensure(F);
-    nsum.ensure(F);
-    mean.ensure(F);
-    if (!replay) scored.ensure(F * (size_t)std::max(k, 1));
-    if (task == TASK_CLS) best_hl.ensure(F * (size_t)C);
-    if (task == TASK_CLSW) dist.ensure(F * (size_t)C);
-  }
-  Search view() {
-    return Search{flag.p,       best_mil.p,   visited.p,    nconst.p,     dc.p,         cand_begin.p,
-                  cand_cnt.p,   best_feature.p, best_nleft.p, split_slot.p, best_score.p, best_cut.p,
-                  total.p,      nsum.p,       mean.p,       scored.p,     best_hl.p,    dist.p};
-  }
-};
-
-struct CandBufs {
-  DevBuf<int32_t> node, feature, cnt_lt, cnt_nan, hist;
-  DevBuf<double> u, cut, score;
-  DevBuf<uint8_t> flags, mil;
-  DevBuf<int64_t> mask_off;
-  void ensure(size_t N, int C, int task) {
-    node.ensure(N);
-    feature.ensure(N);
-    cnt_lt.ensure(N);
-    cnt_nan.ensure(N);
-    u.ensure(N);
-    cut.ensure(N);
-    flags.ensure(N);
-    if (task == TASK_CLS) {
-      hist.ensure(N * 2 * (size_t)C);
-    } else {
-      score.ensure(N);
-      mil.ensure(N);
-      mask_off.ensure(N);
-    }
-  }
-  Cand view() {
-    return Cand{node.p, feature.p, cnt_lt.p, cnt_nan.p, u.p, cut.p, score.p, flags.p, mil.p, hist.p, mask_off.p};
-  }
-};
-
-struct OutBufs {
-  DevBuf<int32_t> feature, left, right;
-  DevBuf<double> cut, leaf;
-  DevBuf<uint8_t> mil;
-  void grow(size_t n, size_t used, int lw, cudaStream_t st) {
-    feature.grow_keep(n, used, st);
-    left.grow_keep(n, used, st);
-    right.grow_keep(n, used, st);
+struct PoolBufs {
+  DevBuf<int32_t> tree, feat, child;
+  DevBuf<double> cut, leaf_vals;
+  void grow(size_t n, size_t used, size_t nleaf, size_t leaf_used, int lw, cudaStream_t st) {
+    tree.grow_keep(n, used, st);
+    feat.grow_keep(n, used, st);
+    child.grow_keep(n, used, st);
     cut.grow_keep(n, used, st);
-    mil.grow_keep(n, used, st);
-    leaf.grow_keep(n * (size_t)lw, used * (size_t)lw, st);
+    leaf_vals.grow_keep(nleaf * (size_t)lw, leaf_used * (size_t)lw, st);
   }
-  Out view() { return Out{feature.p, left.p, right.p, cut.p, leaf.p, mil.p}; }
+  Pool view() { return Pool{tree.p, feat.p, child.p, cut.p, leaf_vals.p}; }
 };
 
+}  // namespace
+
+// Device buffers that survive across builds on one context (no cudaMalloc in the steady state).
+struct Workspace {
+  DevBuf<int32_t> idx[2], yc[2], q[2][2], size, nleaf, pos, lpos;
+  DevBuf<double> yr[2], ws[2];
+  FrontierBufs fr[2];
+  PoolBufs pool;
+  DevBuf<uint32_t> scratch;
+  DevBuf<Counters> cnt;
+  DevBuf<int64_t> tree_off, leaf_off;
+};
+
+void et_workspace_free(Workspace *ws) { delete ws; }
+
+namespace {
+
+struct PhaseTimer {
+  bool on = getenv("ETGPU_TIMING") != nullptr;
+  cudaStream_t st;
+  double acc[8] = {0};
+  std::chrono::steady_clock::time_point t0;
+  void start() {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    t0 = std::chrono::steady_clock::now();
+  }
+  void stop(int k) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    acc[k] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
+  void report() {
+    if (!on) return;
+    static const char *names[] = {"alloc", "init", "node_warp", "node_cta", "sync", "preorder", "final", "other"};
+    fprintf(stderr, "[etgpu timing ms]");
+    for (int i = 0; i < 8; i++) fprintf(stderr, " %s=%.1f", names[i], acc[i]);
+    fprintf(stderr, "\n");
+  }
+};
+
+// CUDA-event spans of the node kernels (summed after the per-level sync)
 struct EventTimer {
   std::vector<cudaEvent_t> pool;
-  std::vector<std::pair<int, int>> spans[2];  // kind 0 = split search, 1 = partition
+  std::vector<std::pair<int, int>> spans[2];  // 0 = warp-owned nodes, 1 = CTA-owned nodes
   size_t used = 0;
   ~EventTimer() {
     for (auto e : pool) cudaEventDestroy(e);
@@ -932,8 +1022,7 @@ struct EventTimer {
     cudaEventRecord(pool[used], st);
     return (int)used++;
   }
-  // call after a stream sync
-  void drain(double *acc) {
+  void drain(double *acc) {  // call after a stream sync
     for (int kx = 0; kx < 2; kx++) {
       for (auto &sp : spans[kx]) {
         float ms = 0.f;
@@ -946,73 +1035,34 @@ struct EventTimer {
   }
 };
 
-template <typename T>
-static T *upload_tmp(const T *h, size_t n, cudaStream_t st) {
-  T *d = nullptr;
-  if (cudaMalloc((void **)&d, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) {
-    cudaGetLastError();
-    ET_FAIL(ET_ENOMEM, "device allocation failed");
+template <int TASK>
+void launch_level(et_ctx *ctx, const P &p, int32_t q0, int32_t q1, size_t smem_warp, size_t smem_cta, PhaseTimer &pt,
+                  EventTimer &et) {
+  cudaStream_t st = ctx->stream;
+  if (q0 > 0) {
+    pt.start();
+    int e0 = et.rec(st);
+    k_node<TASK, 32><<<(unsigned)ceil_div(q0, WARPS_PER_CTA), 32 * WARPS_PER_CTA, smem_warp * WARPS_PER_CTA, st>>>(p, q0);
+    int e1 = et.rec(st);
+    et.spans[0].push_back({e0, e1});
+    ctx->launches++;
+    pt.stop(2);
   }
-  if (n) cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, st);
-  return d;
+  if (q1 > 0) {
+    pt.start();
+    int e0 = et.rec(st);
+    k_node<TASK, CTA_TEAM><<<(unsigned)q1, CTA_TEAM, smem_cta, st>>>(p, q1);
+    int e1 = et.rec(st);
+    et.spans[1].push_back({e0, e1});
+    ctx->launches++;
+    pt.stop(3);
+  }
 }
 
-// BFS-numbered batch output -> per-tree pre-order HostTree
-static void to_preorder(const std::vector<int32_t> &feature, const std::vector<int32_t> &left,
-                        const std::vector<int32_t> &right, const std::vector<double> &cut,
-                        const std::vector<uint8_t> &mil, const std::vector<double> &leaf, int lw, int32_t root,
-                        HostTree &out) {
-  std::vector<int32_t> order;   // batch ids in pre-order
-  std::vector<int32_t> stack;
-  stack.push_back(root);
-  while (!stack.empty()) {
-    int32_t v = stack.back();
-    stack.pop_back();
-    order.push_back(v);
-    if (feature[(size_t)v] >= 0) {
-      stack.push_back(right[(size_t)v]);
-      stack.push_back(left[(size_t)v]);
-    }
-  }
-  size_t n = order.size();
-  out.feature.resize(n);
-  out.left.assign(n, -1);
-  out.right.assign(n, -1);
-  out.cut.resize(n);
-  out.mil.resize(n);
-  out.leaf.assign(n * (size_t)lw, 0.0);
-  // pre-order position of a right child = position right after the whole left subtree; recover
-  // it with a second stack walk that records positions
-  std::vector<std::pair<int32_t, int32_t>> st2;  // (batch id, parent pos or -1) ; sign encodes side
-  size_t pos = 0;
-  struct Fr {
-    int32_t v, parent;
-    bool is_right;
-  };
-  std::vector<Fr> st;
-  st.push_back(Fr{root, -1, false});
-  while (!st.empty()) {
-    Fr fr = st.back();
-    st.pop_back();
-    int32_t me = (int32_t)pos++;
-    size_t v = (size_t)fr.v;
-    if (fr.parent >= 0) {
-      if (fr.is_right)
-        out.right[(size_t)fr.parent] = me;
-      else
-        out.left[(size_t)fr.parent] = me;
-    }
-    out.feature[(size_t)me] = feature[v];
-    out.cut[(size_t)me] = cut[v];
-    out.mil[(size_t)me] = mil[v];
-    if (feature[v] >= 0) {
-      st.push_back(Fr{right[v], me, true});
-      st.push_back(Fr{left[v], me, false});
-    } else {
-      for (int c = 0; c < lw; c++) out.leaf[(size_t)me * lw + c] = leaf[v * (size_t)lw + c];
-    }
-  }
-  (void)st2;
+template <int TASK>
+void set_smem_attr(size_t smem_warp_total, size_t smem_cta) {
+  CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_warp_total));
+  CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, CTA_TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
 }
 
 }  // namespace
@@ -1028,15 +1078,36 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
   const int W = (d + 31) / 32;
   if (a.k < 0) ET_FAIL(ET_EINVAL, "k must be >= 0");
   if (replay && a.replay->n_trees != a.m) ET_FAIL(ET_EREPLAY, "replay trace holds %d trees, m = %d", a.replay->n_trees, a.m);
+  if (!ctx->ws) ctx->ws = new Workspace();
+  Workspace &ws = *ctx->ws;
   et_stats S;
   memset(&S, 0, sizeof(S));
   const int64_t launches0 = ctx->launches;
+  PhaseTimer pt;
+  pt.st = st;
+  EventTimer evt;
+  double tacc[2] = {0, 0};
+
+  // candidates per batch: bounded by 32 lanes and by the team's shared memory
+  int NB = 32;
+  const size_t smem_budget_warp = 40 * 1024, smem_budget_cta = 160 * 1024;
+  while (NB > 1 && ((size_t)make_lay(task, true, C, NB, W, replay).bytes > smem_budget_warp ||
+                    (size_t)make_lay(task, false, C, NB, W, replay).bytes > smem_budget_cta))
+    NB--;
+  const Lay lay_w = make_lay(task, true, C, NB, W, replay), lay_c = make_lay(task, false, C, NB, W, replay);
+  if ((size_t)lay_w.bytes * WARPS_PER_CTA > 200 * 1024 || (size_t)lay_c.bytes > 200 * 1024)
+    ET_FAIL(ET_EUNSUPPORTED, "numClasses=%d / %d features need more shared memory per node than one SM has", C, d);
+  if (task == TASK_CLS)
+    set_smem_attr<TASK_CLS>((size_t)lay_w.bytes * WARPS_PER_CTA, (size_t)lay_c.bytes);
+  else if (task == TASK_CLSW)
+    set_smem_attr<TASK_CLSW>((size_t)lay_w.bytes * WARPS_PER_CTA, (size_t)lay_c.bytes);
+  else
+    set_smem_attr<TASK_REG>((size_t)lay_w.bytes * WARPS_PER_CTA, (size_t)lay_c.bytes);
+
   cudaEvent_t ev0, ev1;
   CUDA_CHECK(cudaEventCreate(&ev0));
   CUDA_CHECK(cudaEventCreate(&ev1));
   CUDA_CHECK(cudaEventRecord(ev0, st));
-  out->trees.clear();
-  out->trees.resize((size_t)a.m);
 
   // the reference's seeding (pkg:629,654-655) names one stream per tree; the free-running GPU RNG
   // is counter based and keyed by (seed, global tree id)
@@ -1046,26 +1117,13 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
     tree_keys[(size_t)t] = et_tree_key((uint64_t)a.seed, gid);
   }
 
-  // batch size: bound the per-sample state (idx + targets, ping-pong) to ~6 GB
+  // batch size: bound the per-sample state (idx + targets, ping-pong) to ~8 GB
   size_t per_sample = 2 * (4 + (task == TASK_REG ? 8 : 4) + (task == TASK_CLSW ? 8 : 0));
-  int64_t max_samples = (int64_t)(((size_t)6 << 30) / per_sample);
+  int64_t max_samples = (int64_t)(((size_t)8 << 30) / per_sample);
   int32_t B = (int32_t)std::max<int64_t>(1, std::min<int64_t>(a.m, max_samples / std::max<int64_t>(n, 1)));
   if (const char *env = getenv("ETGPU_BATCH_TREES")) B = std::max(1, std::min(a.m, atoi(env)));
 
-  DevBuf<int32_t> idx[2], yc[2];
-  DevBuf<double> yr[2], ws[2];
-  LevelBufs lv[2];
-  SearchBufs sb;
-  CandBufs cb[2];
-  OutBufs ob;
-  DevBuf<uint32_t> sidemask;
-  DevBuf<double> wscratch;
-  DevBuf<Counters> cnt;
-  cnt.ensure(1);
-  EventTimer timer;
-  double tacc[2] = {0, 0};
-
-  // root histogram on the device (TASK_CLS)
+  ws.cnt.ensure(1);
   std::vector<int32_t> rh((size_t)std::max(C, 1), 0);
   if (task == TASK_CLS)
     for (int c = 0; c < C; c++) rh[(size_t)c] = (int32_t)D->root_hist[(size_t)c];
@@ -1080,8 +1138,8 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
   if (replay) {
     const et_replay *R = a.replay;
     int64_t nn = R->node_offset[R->n_trees];
-    std::vector<int32_t> l((size_t)nn), r((size_t)nn);
     if (nn > 0x7fffffff) ET_FAIL(ET_EREPLAY, "replay trace too large");
+    std::vector<int32_t> l((size_t)nn), r((size_t)nn);
     for (int t = 0; t < R->n_trees; t++) {
       int64_t o = R->node_offset[t];
       for (int64_t q = o; q < R->node_offset[t + 1]; q++) {
@@ -1103,6 +1161,12 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
     d_tr_cand_flag = upload_tmp(R->cand_flag, (size_t)R->n_cand, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
   }
+  struct Seg {
+    PNode *nodes;
+    double *leaves;
+    int64_t n_nodes, n_leaves;
+  };
+  std::vector<Seg> segs;
   auto free_tmp = [&]() {
     cudaFree(d_root_hist);
     cudaFree(d_tr_cand_begin);
@@ -1116,17 +1180,22 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
     cudaEventDestroy(ev1);
   };
 
+  out->m = a.m;
+  out->tree_off.assign((size_t)a.m + 1, 0);
+  int64_t node_base = 0, leaf_base = 0;  // forest-wide offsets of the current batch
+
   try {
     for (int32_t t0 = 0; t0 < a.m; t0 += B) {
       const int32_t Bt = std::min(B, a.m - t0);
       const size_t ns = (size_t)Bt * (size_t)n;
+      pt.start();
       for (int q = 0; q < 2; q++) {
-        idx[q].ensure(ns, 1.0);
+        ws.idx[q].ensure(ns, 1.0);
         if (task == TASK_REG)
-          yr[q].ensure(ns, 1.0);
+          ws.yr[q].ensure(ns, 1.0);
         else
-          yc[q].ensure(ns, 1.0);
-        if (task == TASK_CLSW) ws[q].ensure(ns, 1.0);
+          ws.yc[q].ensure(ns, 1.0);
+        if (task == TASK_CLSW) ws.ws[q].ensure(ns, 1.0);
       }
       P p;
       memset(&p, 0, sizeof(p));
@@ -1142,150 +1211,94 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       p.W = W;
       p.task = task;
       p.replay = replay ? 1 : 0;
-      p.cnt = cnt.p;
+      p.NB = NB;
+      p.cnt = ws.cnt.p;
       p.tr = Trace{d_tr_cand_begin, d_tr_cand_count, d_tr_left, d_tr_right, d_tr_cand_feature, d_tr_cand_u,
                    d_tr_cand_flag};
-      int srcb = 0;
+      int srcb = 0, cl = 0;
+      int32_t F = Bt;
+      ws.fr[0].ensure((size_t)F, C, W, task == TASK_CLS, !replay);
+      for (int q = 0; q < 2; q++) ws.q[0][q].ensure((size_t)F, 1.5);
+      pt.stop(0);
+      pt.start();
       {
         unsigned grid = (unsigned)std::min<int64_t>(ceil_div((int64_t)ns, 256), (int64_t)ctx->sm_count * 16);
-        k_init_samples<<<std::max(grid, 1u), 256, 0, st>>>(n, Bt, idx[0].p, D->y_cls, task == TASK_REG ? nullptr : yc[0].p,
-                                                          D->y_reg, task == TASK_REG ? yr[0].p : nullptr, D->w,
-                                                          task == TASK_CLSW ? ws[0].p : nullptr);
+        k_init_samples<<<std::max(grid, 1u), 256, 0, st>>>(n, Bt, ws.idx[0].p, D->y_cls,
+                                                          task == TASK_REG ? nullptr : ws.yc[0].p, D->y_reg,
+                                                          task == TASK_REG ? ws.yr[0].p : nullptr, D->w,
+                                                          task == TASK_CLSW ? ws.ws[0].p : nullptr);
         ctx->launches++;
       }
-      int32_t F = Bt;
-      int cl = 0;  // current level buffer
-      lv[cl].ensure((size_t)F, C, W, task == TASK_CLS, !replay);
-      p.cur = lv[cl].view();
+      p.cur = ws.fr[0].view();
+      p.q_cur[0] = ws.q[0][0].p;
+      p.q_cur[1] = ws.q[0][1].p;
       uint64_t *d_keys = upload_tmp(tree_keys.data() + t0, (size_t)Bt, st);
       int64_t *d_troots = replay ? upload_tmp(trace_roots.data() + t0, (size_t)Bt, st) : nullptr;
+      CUDA_CHECK(cudaMemsetAsync(ws.cnt.p, 0, sizeof(Counters), st));
       k_init_roots<<<(unsigned)ceil_div(F, 128), 128, 0, st>>>(p, Bt, d_keys, d_troots, d_root_hist);
       ctx->launches++;
       CUDA_CHECK(cudaStreamSynchronize(st));
       cudaFree(d_keys);
       if (d_troots) cudaFree(d_troots);
-      CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, sizeof(Counters), st));
+      pt.stop(1);
 
-      int64_t n_nodes = Bt;  // output nodes allocated so far (roots)
-      ob.grow((size_t)n_nodes, 0, lw, st);
+      int64_t n_nodes = Bt, n_leaves = 0;
+      std::vector<int32_t> level_start{0};
+      int32_t q0 = n <= NW_MAX ? Bt : 0, q1 = Bt - q0;
+      Counters hc;
+      memset(&hc, 0, sizeof(hc));
       while (F > 0) {
         S.levels++;
-        sb.ensure((size_t)F, C, a.k, task, replay);
-        lv[cl ^ 1].ensure((size_t)F * 2, C, W, task == TASK_CLS, !replay);
-        ob.grow((size_t)(n_nodes + 2 * (int64_t)F), (size_t)n_nodes, lw, st);
-        p.idx_src = idx[srcb].p;
-        p.idx_dst = idx[srcb ^ 1].p;
-        p.yc_src = yc[srcb].p;
-        p.yc_dst = yc[srcb ^ 1].p;
-        p.yr_src = yr[srcb].p;
-        p.yr_dst = yr[srcb ^ 1].p;
-        p.w_src = ws[srcb].p;
-        p.w_dst = ws[srcb ^ 1].p;
-        p.cur = lv[cl].view();
-        p.nxt = lv[cl ^ 1].view();
-        p.s = sb.view();
-        p.o = ob.view();
+        pt.start();
+        ws.fr[cl ^ 1].ensure((size_t)F * 2, C, W, task == TASK_CLS, !replay);
+        for (int q = 0; q < 2; q++) ws.q[cl ^ 1][q].ensure((size_t)F * 2, 1.5);
+        ws.pool.grow((size_t)(n_nodes + 2 * (int64_t)F), (size_t)n_nodes, (size_t)(n_leaves + F), (size_t)n_leaves, lw, st);
+        if (task != TASK_CLS && q1 > 0)
+          ws.scratch.ensure((size_t)NB * 2 * ((size_t)Bt * (size_t)n / 32 + (size_t)q1 + 1) + 64, 1.0);
+        pt.stop(0);
+        p.idx_src = ws.idx[srcb].p;
+        p.idx_dst = ws.idx[srcb ^ 1].p;
+        p.yc_src = ws.yc[srcb].p;
+        p.yc_dst = ws.yc[srcb ^ 1].p;
+        p.yr_src = ws.yr[srcb].p;
+        p.yr_dst = ws.yr[srcb ^ 1].p;
+        p.w_src = ws.ws[srcb].p;
+        p.w_dst = ws.ws[srcb ^ 1].p;
+        p.cur = ws.fr[cl].view();
+        p.nxt = ws.fr[cl ^ 1].view();
+        p.q_cur[0] = ws.q[cl][0].p;
+        p.q_cur[1] = ws.q[cl][1].p;
+        p.q_nxt[0] = ws.q[cl ^ 1][0].p;
+        p.q_nxt[1] = ws.q[cl ^ 1][1].p;
+        p.o = ws.pool.view();
+        p.scratch = ws.scratch.p;
         p.node_base_next = (int32_t)n_nodes;
-        const unsigned gF = (unsigned)ceil_div(F, 128);
         if (task == TASK_CLS)
-          k_classify_cls<<<gF, 128, 0, st>>>(p, F);
-        else if (task == TASK_REG)
-          k_classify_reg<<<gF, 128, 0, st>>>(p, F);
+          launch_level<TASK_CLS>(ctx, p, q0, q1, (size_t)lay_w.bytes, (size_t)lay_c.bytes, pt, evt);
+        else if (task == TASK_CLSW)
+          launch_level<TASK_CLSW>(ctx, p, q0, q1, (size_t)lay_w.bytes, (size_t)lay_c.bytes, pt, evt);
         else
-          k_classify_clsw<<<gF, 128, 0, st>>>(p, F);
-        ctx->launches++;
-        // candidate rounds
-        size_t cand_cap = (size_t)F * (size_t)std::max(a.k, 1);
-        if (replay) {
-          // a node's trace may hold more than k draws (constant hits): bound by the largest count
-          cand_cap = (size_t)a.replay->n_cand;
-        }
-        for (int q = 0; q < 2; q++) cb[q].ensure(cand_cap, C, task);
-        p.c[0] = cb[0].view();
-        p.c[1] = cb[1].view();
-        for (int round = 0;; round++) {
-          const int cur = round & 1;
-          Counters hc;
-          // reset this round's counters (n_cand[cur], mask_words)
-          CUDA_CHECK(cudaMemsetAsync(&cnt.p->n_cand[cur], 0, sizeof(int32_t), st));
-          CUDA_CHECK(cudaMemsetAsync(&cnt.p->mask_words, 0, sizeof(unsigned long long), st));
-          k_update_draw<<<gF, 128, 0, st>>>(p, F, round);
-          ctx->launches++;
-          CUDA_CHECK(cudaMemcpyAsync(&hc, cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-          CUDA_CHECK(cudaStreamSynchronize(st));
-          const int32_t nc = hc.n_cand[cur];
-          if (nc == 0) break;
-          S.rounds++;
-          if ((size_t)nc > cand_cap) ET_FAIL(ET_ECUDA, "internal: candidate buffer overflow (%d > %zu)", nc, cand_cap);
-          if (task != TASK_CLS) {
-            sidemask.ensure((size_t)hc.mask_words + 64);
-            p.sidemask = sidemask.p;
-            if (task == TASK_CLSW) {
-              wscratch.ensure((size_t)nc * 2 * (size_t)C);
-              p.wscratch = wscratch.p;
-            }
-          }
-          const int wpb = 8;
-          const unsigned gi = (unsigned)ceil_div(nc, wpb);
-          int e0 = timer.rec(st);
-          if (task == TASK_CLS) {
-            size_t smem = (size_t)wpb * 2 * C * sizeof(int32_t);
-            if (smem > 48 * 1024)
-              CUDA_CHECK(cudaFuncSetAttribute(k_items_warp<TASK_CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)smem));
-            k_items_warp<TASK_CLS><<<gi, wpb * 32, smem, st>>>(p, nc, cur);
-          } else {
-            k_items_warp<TASK_REG><<<gi, wpb * 32, 0, st>>>(p, nc, cur);
-          }
-          ctx->launches++;
-          if (task == TASK_REG) {
-            k_score_reg<<<(unsigned)ceil_div(nc, 64), 64, 0, st>>>(p, nc, cur);
-            ctx->launches++;
-          } else if (task == TASK_CLSW) {
-            k_score_clsw<<<(unsigned)ceil_div(nc, 64), 64, 0, st>>>(p, nc, cur);
-            ctx->launches++;
-          }
-          int e1 = timer.rec(st);
-          timer.spans[0].push_back({e0, e1});
-          CUDA_CHECK(cudaGetLastError());
-        }
-        // finalize + partition
-        k_finalize<<<gF, 128, 0, st>>>(p, F);
-        ctx->launches++;
-        Counters hc;
-        CUDA_CHECK(cudaMemcpyAsync(&hc, cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+          launch_level<TASK_REG>(ctx, p, q0, q1, (size_t)lay_w.bytes, (size_t)lay_c.bytes, pt, evt);
+        pt.start();
+        CUDA_CHECK(cudaMemcpyAsync(&hc, ws.cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        // the next level starts from clean per-level counters (leaf count and stats keep accumulating)
+        CUDA_CHECK(cudaMemsetAsync(ws.cnt.p, 0, offsetof(Counters, n_leaves), st));
+        CUDA_CHECK(cudaMemsetAsync(&ws.cnt.p->scratch_words, 0, sizeof(unsigned long long), st));
         CUDA_CHECK(cudaStreamSynchronize(st));
-        timer.drain(tacc);
+        CUDA_CHECK(cudaGetLastError());
+        evt.drain(tacc);
+        pt.stop(4);
         const int32_t nf = hc.next_f;
-        if (nf > 0) {
-          int e0 = timer.rec(st);
-          k_partition_warp<<<(unsigned)ceil_div(F, 8), 256, 0, st>>>(p, F);
-          ctx->launches++;
-          int e1 = timer.rec(st);
-          timer.spans[1].push_back({e0, e1});
-          srcb ^= 1;
-        }
-        CUDA_CHECK(cudaMemsetAsync(&cnt.p->next_f, 0, sizeof(int32_t), st));
+        n_leaves = hc.n_leaves;
+        level_start.push_back((int32_t)n_nodes);
         n_nodes += nf;
         if (n_nodes > 0x7ffffff0) ET_FAIL(ET_EUNSUPPORTED, "batch exceeds 2^31 nodes; lower ETGPU_BATCH_TREES");
+        q0 = hc.q_count[0];
+        q1 = hc.q_count[1];
+        if (nf > 0) srcb ^= 1;
         F = nf;
         cl ^= 1;
-        CUDA_CHECK(cudaGetLastError());
       }
-      // batch output -> host, BFS numbering -> per-tree pre-order
-      Counters hc;
-      CUDA_CHECK(cudaMemcpyAsync(&hc, cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-      std::vector<int32_t> hf((size_t)n_nodes), hl((size_t)n_nodes), hr((size_t)n_nodes);
-      std::vector<double> hcut((size_t)n_nodes), hleaf((size_t)n_nodes * (size_t)lw);
-      std::vector<uint8_t> hmil((size_t)n_nodes);
-      CUDA_CHECK(cudaMemcpyAsync(hf.data(), ob.feature.p, hf.size() * 4, cudaMemcpyDeviceToHost, st));
-      CUDA_CHECK(cudaMemcpyAsync(hl.data(), ob.left.p, hl.size() * 4, cudaMemcpyDeviceToHost, st));
-      CUDA_CHECK(cudaMemcpyAsync(hr.data(), ob.right.p, hr.size() * 4, cudaMemcpyDeviceToHost, st));
-      CUDA_CHECK(cudaMemcpyAsync(hcut.data(), ob.cut.p, hcut.size() * 8, cudaMemcpyDeviceToHost, st));
-      CUDA_CHECK(cudaMemcpyAsync(hmil.data(), ob.mil.p, hmil.size(), cudaMemcpyDeviceToHost, st));
-      CUDA_CHECK(cudaMemcpyAsync(hleaf.data(), ob.leaf.p, hleaf.size() * 8, cudaMemcpyDeviceToHost, st));
-      CUDA_CHECK(cudaStreamSynchronize(st));
-      timer.drain(tacc);
       S.v_mm += (int64_t)hc.st[ST_VMM];
       S.v_sc += (int64_t)hc.st[ST_VSC];
       S.s_rows += (int64_t)hc.st[ST_SROWS];
@@ -1295,19 +1308,104 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       S.scored += (int64_t)hc.st[ST_SCORED];
       S.replay_mismatches += (int64_t)hc.st[ST_MISMATCH];
       S.nodes += n_nodes;
-      for (int32_t t = 0; t < Bt; t++)
-        to_preorder(hf, hl, hr, hcut, hmil, hleaf, lw, t, out->trees[(size_t)(t0 + t)]);
+      // ---- creation order -> per-tree pre-order, on the device
+      pt.start();
+      ws.size.ensure((size_t)n_nodes);
+      ws.nleaf.ensure((size_t)n_nodes);
+      ws.pos.ensure((size_t)n_nodes);
+      ws.lpos.ensure((size_t)n_nodes);
+      ws.tree_off.ensure((size_t)Bt + 1);
+      ws.leaf_off.ensure((size_t)Bt + 1);
+      Pool po = ws.pool.view();
+      // level l holds node ids [level_start[l], level_start[l+1]) (the last entry closes the list)
+      const int nlev = (int)level_start.size() - 1;
+      for (int l = nlev - 1; l >= 0; l--) {
+        int32_t lo = level_start[(size_t)l], hi = level_start[(size_t)l + 1];
+        if (hi <= lo) continue;
+        k_subtree_sizes<<<(unsigned)ceil_div(hi - lo, 256), 256, 0, st>>>(po, lo, hi, ws.size.p, ws.nleaf.p);
+        ctx->launches++;
+      }
+      k_root_offsets<<<1, 32, 0, st>>>(Bt, ws.size.p, ws.nleaf.p, node_base, leaf_base, ws.tree_off.p, ws.leaf_off.p,
+                                       ws.pos.p, ws.lpos.p);
+      ctx->launches++;
+      for (int l = 0; l < nlev; l++) {
+        int32_t lo = level_start[(size_t)l], hi = level_start[(size_t)l + 1];
+        if (hi <= lo) continue;
+        k_assign_pos<<<(unsigned)ceil_div(hi - lo, 256), 256, 0, st>>>(po, lo, hi, ws.size.p, ws.nleaf.p, ws.pos.p,
+                                                                      ws.lpos.p);
+        ctx->launches++;
+      }
+      Seg sg;
+      sg.n_nodes = n_nodes;
+      sg.n_leaves = n_leaves;
+      sg.nodes = nullptr;
+      sg.leaves = nullptr;
+      if (cudaMalloc((void **)&sg.nodes, (size_t)n_nodes * sizeof(PNode)) != cudaSuccess ||
+          cudaMalloc((void **)&sg.leaves, std::max<size_t>(1, (size_t)n_leaves * lw) * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        if (sg.nodes) cudaFree(sg.nodes);
+        ET_FAIL(ET_ENOMEM, "cannot allocate the forest (%lld nodes)", (long long)n_nodes);
+      }
+      segs.push_back(sg);
+      k_scatter<<<(unsigned)ceil_div(n_nodes, 256), 256, 0, st>>>(po, (int32_t)n_nodes, lw, ws.pos.p, ws.lpos.p,
+                                                                  ws.tree_off.p, ws.leaf_off.p, node_base, leaf_base,
+                                                                  sg.nodes, sg.leaves);
+      ctx->launches++;
+      std::vector<int64_t> toff((size_t)Bt + 1);
+      CUDA_CHECK(cudaMemcpyAsync(toff.data(), ws.tree_off.p, ((size_t)Bt + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      CUDA_CHECK(cudaGetLastError());
+      for (int32_t t = 0; t <= Bt; t++) out->tree_off[(size_t)(t0 + t)] = toff[(size_t)t];
+      node_base += n_nodes;
+      leaf_base += n_leaves;
+      pt.stop(5);
     }
+    // ---- the forest stays resident in HBM; batches are concatenated
+    pt.start();
+    out->total_nodes = node_base;
+    out->total_leaves = leaf_base;
+    if (segs.size() == 1) {
+      out->d_nodes = segs[0].nodes;
+      out->d_leaf = segs[0].leaves;
+      segs.clear();
+    } else {
+      CUDA_CHECK(cudaMalloc((void **)&out->d_nodes, std::max<size_t>(1, (size_t)node_base) * sizeof(PNode)));
+      CUDA_CHECK(cudaMalloc((void **)&out->d_leaf, std::max<size_t>(1, (size_t)leaf_base * lw) * sizeof(double)));
+      int64_t no = 0, lo = 0;
+      for (auto &sg : segs) {
+        CUDA_CHECK(cudaMemcpyAsync(out->d_nodes + no, sg.nodes, (size_t)sg.n_nodes * sizeof(PNode),
+                                   cudaMemcpyDeviceToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(out->d_leaf + lo * lw, sg.leaves, (size_t)sg.n_leaves * lw * sizeof(double),
+                                   cudaMemcpyDeviceToDevice, st));
+        no += sg.n_nodes;
+        lo += sg.n_leaves;
+      }
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      for (auto &sg : segs) {
+        cudaFree(sg.nodes);
+        cudaFree(sg.leaves);
+      }
+      segs.clear();
+    }
+    CUDA_CHECK(cudaMalloc((void **)&out->d_tree_off, ((size_t)a.m + 1) * sizeof(int64_t)));
+    CUDA_CHECK(cudaMemcpyAsync(out->d_tree_off, out->tree_off.data(), ((size_t)a.m + 1) * sizeof(int64_t),
+                               cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaEventRecord(ev1, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
+    pt.stop(6);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
     S.gpu_ms = ms;
-    S.gpu_ms_split = tacc[0];
-    S.gpu_ms_partition = tacc[1];
+    S.gpu_ms_split = tacc[0] + tacc[1];  // node kernels: split search + partition fused
+    S.gpu_ms_partition = tacc[1];        // of which CTA-owned (large) nodes
     S.launches = ctx->launches - launches0;
+    pt.report();
   } catch (...) {
     cudaStreamSynchronize(st);
+    for (auto &sg : segs) {
+      cudaFree(sg.nodes);
+      cudaFree(sg.leaves);
+    }
     free_tmp();
     throw;
   }

@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 
+struct Workspace;  // build.cu: device buffers reused across builds
+
 struct et_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
@@ -9,7 +11,9 @@ struct et_ctx {
   int sm_count = 148;
   std::mutex mu;  // a context serialises its calls
   int64_t launches = 0;
+  Workspace *ws = nullptr;
 };
+void et_workspace_free(Workspace *ws);
 
 struct et_data {
   et_ctx *ctx = nullptr;
@@ -25,32 +29,36 @@ struct et_data {
   std::vector<int64_t> root_hist;  // class counts of the whole table
 };
 
-// One tree, pre-order (the wire format of et_forest_export).
-struct HostTree {
-  std::vector<int32_t> feature, left, right;
-  std::vector<double> cut;
-  std::vector<uint8_t> mil;
-  std::vector<double> leaf;  // n_nodes x leaf_width
+// Device forest node: all trees concatenated in pre-order, one 16-byte node fetched with a single
+// 128-bit load.  Pre-order makes the left child implicit (node + 1), so only the right child is
+// stored (tree-local id).  For a leaf, feat == -1 and right_or_leaf is the forest-wide leaf index
+// into the compact leaf table (leaf_width doubles per leaf, leaves numbered in pre-order).
+// splitMissingIsLess rides in bit 30 of feat.
+struct __align__(16) PNode {
+  double cut;
+  int32_t feat;
+  int32_t right_or_leaf;
 };
+#define ET_MIL_BIT 0x40000000
 
 struct et_forest {
   et_ctx *ctx = nullptr;
   int32_t leaf_width = 1;
   int32_t is_regression = 0;
-  std::vector<HostTree> trees;
-  // device copy for predict (built lazily): trees concatenated
-  bool dev_ready = false;
-  int64_t total_nodes = 0;
-  int32_t max_depth = 0;
-  int64_t *d_tree_off = nullptr;  // m+1
-  int32_t *d_feature = nullptr;
-  double *d_cut = nullptr;
-  int32_t *d_left = nullptr;   // left child (tree-local); right = stored separately
-  int32_t *d_right = nullptr;
-  uint8_t *d_mil = nullptr;
-  double *d_leaf = nullptr;    // total_nodes x leaf_width
+  int32_t m = 0;
+  int64_t total_nodes = 0, total_leaves = 0;
+  std::vector<int64_t> tree_off;  // m + 1, node offsets (host copy)
+  // device-resident forest (what predict traverses)
+  int64_t *d_tree_off = nullptr;  // m + 1
+  PNode *d_nodes = nullptr;       // total_nodes
+  double *d_leaf = nullptr;       // total_leaves x leaf_width
+  // lazily fetched host copy (export)
+  bool host_ready = false;
+  std::vector<PNode> h_nodes;
+  std::vector<double> h_leaf;
   ~et_forest();
 };
+void et_forest_fetch(et_forest *f);  // device -> host copy for export (api.cu)
 
 struct BuildArgs {
   int task;  // 0 cls unweighted, 1 cls weighted, 2 regression
@@ -63,7 +71,6 @@ struct BuildArgs {
 // build.cu
 void et_build_forest(et_ctx *ctx, et_data *data, const BuildArgs &a, et_forest *out, et_stats *stats);
 // predict.cu
-void et_forest_upload(et_ctx *ctx, et_forest *f);
 void et_predict_device_impl(et_ctx *ctx, et_forest *f, const double *x_dev, int64_t n, int32_t d,
                             double *out_dev, int sum_only);
 // api.cu
