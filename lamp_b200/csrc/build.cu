@@ -37,14 +37,18 @@ enum { TASK_CLS = 0, TASK_CLSW = 1, TASK_REG = 2 };
 enum { CF_CONST = 1, CF_NAN = 2, CF_MIL = 4 };
 enum { ST_VMM = 0, ST_VSC, ST_SROWS, ST_PROWS, ST_DRAWS, ST_CONST, ST_SCORED, ST_MISMATCH, ST_COUNT };
 
-constexpr int NW_MAX = 1024;      // nodes up to this many samples are owned by one warp
+constexpr int NT_MAX = 32;        // "tiny" nodes: one warp per node, one LANE per candidate
+constexpr int NW_MAX = 1024;      // nodes up to this many samples are owned by one warp (lanes on samples)
 constexpr int BITS_W = NW_MAX / 32;
 constexpr int CTA_TEAM = 512;     // threads of the CTA that owns a larger node
 constexpr int WARPS_PER_CTA = 4;  // warp teams per CTA in the small-node kernel
 
+constexpr int NQ = 3;  // size classes: 0 tiny, 1 warp, 2 CTA
+__host__ __device__ inline int size_class(int64_t n) { return n <= NT_MAX ? 0 : (n <= NW_MAX ? 1 : 2); }
+
 struct Counters {
   int32_t next_f;
-  int32_t q_count[2];
+  int32_t q_count[NQ];
   int32_t n_leaves;
   unsigned long long scratch_words;
   unsigned long long st[ST_COUNT];
@@ -127,7 +131,7 @@ struct P {
   int32_t *idx_src, *idx_dst, *yc_src, *yc_dst;
   double *yr_src, *yr_dst, *w_src, *w_dst;
   Frontier cur, nxt;
-  int32_t *q_cur[2], *q_nxt[2];
+  int32_t *q_cur[NQ], *q_nxt[NQ];
   Pool o;
   Trace tr;
   Counters *cnt;
@@ -168,7 +172,7 @@ __global__ void k_init_roots(P p, int32_t B, const uint64_t *tree_keys, const in
       p.cur.mask[(int64_t)t * p.W + w] = m;
     }
   }
-  p.q_cur[p.n <= NW_MAX ? 0 : 1][t] = t;
+  p.q_cur[size_class(p.n)][t] = t;
 }
 
 // ---- team helpers ---------------------------------------------------------------------------
@@ -368,7 +372,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
   uint32_t *s_bits = reinterpret_cast<uint32_t *>(smi + L.o_bits);
   int32_t *s_misc = smi + L.o_misc;
 
-  const int i = p.q_cur[WARP ? 0 : 1][q];
+  const int i = p.q_cur[WARP ? 1 : 2][q];
   const int32_t tree = p.cur.tree[i], b = p.cur.begin[i], e = p.cur.end[i], n = e - b;
   const int32_t node = p.cur.node[i], depth = p.cur.depth[i];
   const int64_t tn = p.cur.trace[i];
@@ -775,7 +779,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
       if (p.replay && tn >= 0) tc = side ? p.tr.right[tn] : p.tr.left[tn];
       p.nxt.trace[s2] = tc;
       const int32_t cn = side ? (n - nl) : nl;
-      const int qc = cn <= NW_MAX ? 0 : 1;
+      const int qc = size_class(cn);
       p.q_nxt[qc][atomicAdd(&p.cnt->q_count[qc], 1)] = s2;
     }
     atomicAdd(&p.cnt->st[ST_PROWS], (unsigned long long)n);
@@ -848,6 +852,471 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
       }
       lpos += ltot;
       rpos += rtot;
+    }
+  }
+}
+
+
+// ---- tiny nodes (n <= 32): one warp per node, one LANE PER CANDIDATE ---------------------------
+// The node's rows sit in registers (lane j holds sample j); a batch of up to 32 candidate features
+// is evaluated with every lane walking the node's samples for its own candidate: gather once into
+// shared memory, min/max, cutpoint, side bitmask over the samples, exact score from the bitmask.
+// No cross-lane reductions at all; the winner's bitmask IS the partition.
+constexpr int TINY_WARPS = 4;
+
+__host__ __device__ inline int tiny_smem_bytes(int task, int C, int W, bool replay) {
+  int o = NT_MAX * 32;                       // s_x   doubles [sample][lane]
+  o += (task == TASK_CLS) ? 0 : NT_MAX;      // s_y   doubles (regression target / weight)
+  o += (task == TASK_REG) ? 0 : C;           // s_dist doubles
+  int oi = o * 2;
+  oi += (task == TASK_REG) ? 0 : C;          // s_cm  class bitmasks over the samples
+  oi += (task == TASK_CLS) ? C : 0;          // s_hnode
+  oi += replay ? 0 : 2 * W;                  // const / taken masks
+  return ((oi + 3) / 4) * 16;
+}
+
+// position of the r-th set bit of z (r < popc(z))
+__device__ __forceinline__ int select_bit32(uint32_t z, int r) {
+  int pos = 0;
+#pragma unroll
+  for (int w = 16; w > 0; w >>= 1) {
+    const int c = __popc(z & ((1u << w) - 1u));
+    if (r >= c) {
+      r -= c;
+      z >>= w;
+      pos += w;
+    }
+  }
+  return pos;
+}
+
+__device__ __forceinline__ int32_t rank_select_clear_fast(const uint32_t *taken, int W, int32_t rank) {
+  for (int w = 0; w < W; w++) {
+    const uint32_t z = ~taken[w];
+    const int c = __popc(z);
+    if (rank < c) return w * 32 + select_bit32(z, rank);
+    rank -= c;
+  }
+  return -1;
+}
+
+// giniScore from a side bitmask (bit j = sample j goes left) and per-class sample bitmasks.
+// Classes absent from the node contribute exactly +0.0 to both sums and are skipped; an empty side
+// gives 0/0 = NaN exactly like the reference (pkg:1148-1157).
+__device__ __forceinline__ double gini_score_bits(uint32_t in_mask, const uint32_t *cm, int C, int32_t n, double G) {
+  const int32_t cin_i = __popc(in_mask);
+  if (cin_i == 0 || cin_i == n) return NAN;
+  const double cin = (double)cin_i, cout = (double)(n - cin_i), N = (double)n;
+  double sin_ = 0.0, sout = 0.0;
+  for (int c = 0; c < C; c++) {
+    const uint32_t m = cm[c];
+    if (m == 0) continue;
+    const int32_t hi = __popc(m & in_mask), ho = __popc(m) - hi;
+    const double pi = ET_DIV((double)hi, cin), po = ET_DIV((double)ho, cout);
+    sin_ = ET_ADD(sin_, ET_MUL(pi, pi));
+    sout = ET_ADD(sout, ET_MUL(po, po));
+  }
+  const double gin = ET_SUB(1.0, sin_), gout = ET_SUB(1.0, sout);
+  return ET_SUB(ET_SUB(G, ET_DIV(ET_MUL(gin, cin), N)), ET_DIV(ET_MUL(gout, cout), N));
+}
+
+// weighted giniScore (pkg:1132-1157): per-class and per-side sums in subset order.  Each of the
+// reference's accumulators only ever sees its own samples, so walking the samples class by class
+// (in subset order inside a class) performs the same additions in the same order.
+__device__ __forceinline__ double gini_score_w_bits(uint32_t in_mask, const uint32_t *cm, const double *w, int C,
+                                                   int32_t n, double G, double N) {
+  double cin = 0.0, cout = 0.0;
+  for (int j = 0; j < n; j++) {
+    if ((in_mask >> j) & 1u)
+      cin = ET_ADD(cin, w[j]);
+    else
+      cout = ET_ADD(cout, w[j]);
+  }
+  double sin_ = 0.0, sout = 0.0;
+  for (int c = 0; c < C; c++) {
+    uint32_t m = cm[c];
+    double hi = 0.0, ho = 0.0;
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      if ((in_mask >> j) & 1u)
+        hi = ET_ADD(hi, w[j]);
+      else
+        ho = ET_ADD(ho, w[j]);
+    }
+    const double pi = ET_DIV(hi, cin), po = ET_DIV(ho, cout);
+    sin_ = ET_ADD(sin_, ET_MUL(pi, pi));
+    sout = ET_ADD(sout, ET_MUL(po, po));
+  }
+  const double gin = ET_SUB(1.0, sin_), gout = ET_SUB(1.0, sout);
+  return ET_SUB(ET_SUB(G, ET_DIV(ET_MUL(gin, cin), N)), ET_DIV(ET_MUL(gout, cout), N));
+}
+
+// computeVarianceReduction (pkg:1196-1218) from a side bitmask, sequential in subset order
+__device__ __forceinline__ double var_reduction_bits(uint32_t in_mask, const double *y, int32_t n, double V) {
+  double sin_ = 0.0, sout = 0.0;
+  for (int j = 0; j < n; j++) {
+    if ((in_mask >> j) & 1u)
+      sin_ = ET_ADD(sin_, y[j]);
+    else
+      sout = ET_ADD(sout, y[j]);
+  }
+  const int32_t nin = __popc(in_mask), nout = n - nin;
+  const double dnin = (double)nin, dnout = (double)nout, dn = (double)n;
+  const double min_ = ET_DIV(sin_, dnin), mout = ET_DIV(sout, dnout);
+  double qin = 0.0, qout = 0.0;
+  for (int j = 0; j < n; j++) {
+    if ((in_mask >> j) & 1u) {
+      const double dl = ET_SUB(y[j], min_);
+      qin = ET_ADD(qin, ET_MUL(dl, dl));
+    } else {
+      const double dl = ET_SUB(y[j], mout);
+      qout = ET_ADD(qout, ET_MUL(dl, dl));
+    }
+  }
+  const double svin = nin < 1 ? NAN : (nin == 1 ? 0.0 : ET_DIV(qin, ET_SUB(dnin, 1.0)));
+  const double svout = nout < 1 ? NAN : (nout == 1 ? 0.0 : ET_DIV(qout, ET_SUB(dnout, 1.0)));
+  const double vin = (nin == 1) ? 0.0 : ET_DIV(ET_MUL(svin, ET_SUB(dnin, 1.0)), dnin);
+  const double vout = (nout == 1) ? 0.0 : ET_DIV(ET_MUL(svout, ET_SUB(dnout, 1.0)), dnout);
+  const double a = ET_MUL(ET_DIV(dnin, dn), vin);
+  const double bq = ET_MUL(ET_DIV(dnout, dn), vout);
+  return ET_DIV(ET_SUB(ET_SUB(V, a), bq), V);
+}
+
+template <int TASK>
+__global__ void __launch_bounds__(32 * TINY_WARPS) k_node_tiny(P p, int32_t qcount) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tic = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * TINY_WARPS + tic;
+  if (q >= qcount) return;
+  const int C = p.C, W = p.W;
+  unsigned char *sm = smem_raw + (size_t)tic * tiny_smem_bytes(TASK, C, W, p.replay != 0);
+  double *s_x = reinterpret_cast<double *>(sm);
+  double *s_y = s_x + NT_MAX * 32;
+  double *s_dist = s_y + ((TASK == TASK_CLS) ? 0 : NT_MAX);
+  uint32_t *s_cm = reinterpret_cast<uint32_t *>(s_dist + ((TASK == TASK_REG) ? 0 : C));
+  int32_t *s_hnode = reinterpret_cast<int32_t *>(s_cm + ((TASK == TASK_REG) ? 0 : C));
+  uint32_t *s_const = reinterpret_cast<uint32_t *>(s_hnode + ((TASK == TASK_CLS) ? C : 0)), *s_taken = s_const + W;
+
+  const int i = p.q_cur[0][q];
+  const int32_t tree = p.cur.tree[i], b = p.cur.begin[i], e = p.cur.end[i], n = e - b;
+  const int32_t node = p.cur.node[i], depth = p.cur.depth[i];
+  const int64_t tn = p.cur.trace[i];
+  const uint64_t key = p.cur.key[i];
+  const int64_t base = (int64_t)tree * p.n;
+  const int lw = (TASK == TASK_REG) ? 1 : C;
+  const uint32_t nmask = (n >= 32) ? 0xffffffffu : ((1u << n) - 1u);
+
+  // the node's samples: lane j holds sample j
+  const bool has = lane < n;
+  const int32_t row = has ? p.idx_src[base + b + lane] : 0;
+  int32_t cls = -1;
+  double yv = 0.0, wv = 0.0;
+  if (TASK != TASK_REG) {
+    if (has) cls = p.yc_src[base + b + lane];
+    for (int c = lane; c < C; c += 32) s_cm[c] = 0u;
+    __syncwarp();
+    if (has) atomicOr(&s_cm[cls], 1u << lane);
+  }
+  if (TASK == TASK_REG) {
+    if (has) yv = p.yr_src[base + b + lane];
+    s_y[lane] = yv;
+  }
+  if (TASK == TASK_CLSW) {
+    if (has) wv = p.w_src[base + b + lane];
+    s_y[lane] = wv;
+  }
+  __syncwarp();
+
+  // ---------------- stop rules + node totals ----------------
+  bool leaf;
+  double total = 0.0, nsum = (double)n, leaf_mean = 0.0;
+  if (TASK == TASK_CLS) {
+    for (int c = lane; c < C; c += 32) s_hnode[c] = __popc(s_cm[c]);
+    const int32_t cls0 = __shfl_sync(0xffffffffu, cls, 0);  // (never inside a short-circuit: all lanes shuffle)
+    const bool pure = __all_sync(0xffffffffu, !has || cls == cls0);
+    leaf = (p.n_table < p.n_min) || (depth >= p.max_depth) || pure;
+    __syncwarp();
+    if (!leaf) {
+      const double inv = ET_DIV(1.0, (double)n);
+      for (int c = lane; c < C; c += 32) s_dist[c] = et_repeat_add(inv, s_hnode[c]);
+      __syncwarp();
+      double s = 0.0;
+      for (int c = 0; c < C; c++) s = ET_ADD(s, ET_MUL(s_dist[c], s_dist[c]));
+      total = ET_SUB(1.0, s);
+    }
+  } else if (TASK == TASK_REG) {
+    const double head = __shfl_sync(0xffffffffu, yv, 0);
+    const bool uni = __all_sync(0xffffffffu, !has || !(yv != head));
+    leaf = (n < p.n_min) || (depth >= p.max_depth) || uni;
+    double sum = 0.0;
+    for (int j = 0; j < n; j++) sum = ET_ADD(sum, s_y[j]);
+    const double dn = (double)n;
+    leaf_mean = ET_DIV(sum, dn);
+    if (!leaf) {
+      double var = 0.0;
+      if (n > 1) {
+        double qq = 0.0;
+        for (int j = 0; j < n; j++) {
+          const double dl = ET_SUB(s_y[j], leaf_mean);
+          qq = ET_ADD(qq, ET_MUL(dl, dl));
+        }
+        var = ET_DIV(qq, ET_SUB(dn, 1.0));
+      }
+      total = ET_DIV(ET_MUL(var, ET_SUB(dn, 1.0)), dn);
+    }
+  } else {
+    const int32_t cls0 = __shfl_sync(0xffffffffu, cls, 0);
+    const bool uni = __all_sync(0xffffffffu, !has || cls == cls0);
+    leaf = (p.n_table < p.n_min) || (depth >= p.max_depth) || uni;
+    // weighted distribution (pkg:913-927): per-class sums and the total, each in subset order
+    double s = 0.0;
+    for (int j = 0; j < n; j++) s = ET_ADD(s, s_y[j]);
+    for (int c = lane; c < C; c += 32) {
+      uint32_t m = s_cm[c];
+      double a = 0.0;
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        a = ET_ADD(a, s_y[j]);
+      }
+      s_dist[c] = ET_DIV(a, s);
+    }
+    __syncwarp();
+    double sq = 0.0;
+    for (int c = 0; c < C; c++) sq = ET_ADD(sq, ET_MUL(s_dist[c], s_dist[c]));
+    total = ET_SUB(1.0, sq);
+    nsum = s;
+  }
+
+  // ---------------- split search ----------------
+  int32_t visited = 0, nconst = 0, best_feature = -1, best_mil = 0;
+  uint32_t best_mask = 0;
+  double best_score = -INFINITY, best_cut = NAN;
+  unsigned long long st_draws = 0, st_const = 0, st_scored = 0, st_mismatch = 0;
+  if (!leaf) {
+    int32_t dc = 0, tpos = 0, tcnt = 0;
+    int64_t tb = 0;
+    if (p.replay) {
+      if (tn >= 0) {
+        tb = p.tr.cand_begin[tn];
+        tcnt = p.tr.cand_count[tn];
+      }
+    } else {
+      int nc = 0;
+      for (int w = lane; w < W; w += 32) {
+        const uint32_t m = p.cur.mask[(int64_t)i * W + w];
+        s_const[w] = m;
+        s_taken[w] = m;
+        nc += __popc(m);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) nc += __shfl_xor_sync(0xffffffffu, nc, o);
+      nconst = nc - (W * 32 - p.d);
+      __syncwarp();
+    }
+    for (;;) {
+      int32_t nb;
+      const int32_t avail = p.d - nconst - visited;
+      if (p.replay)
+        nb = min(32, tcnt - tpos);
+      else
+        nb = min(32, min(p.k - visited, avail));
+      if (nb <= 0) break;
+      // ---- draw: lane == candidate
+      int32_t f = -1;
+      double u = 0.0;
+      int expect = 0;
+      if (p.replay) {
+        if (lane < nb) {
+          f = p.tr.cand_feature[tb + tpos + lane];
+          u = p.tr.cand_u[tb + tpos + lane];
+          expect = p.tr.cand_flag[tb + tpos + lane] + 1;
+        }
+        tpos += nb;
+      } else {
+        int32_t pick = -1 - lane;
+        if (lane < nb) {
+          const uint64_t r = et_draw(key, (uint32_t)(dc + 2 * lane));
+          pick = rank_select_clear_fast(s_taken, W, (int32_t)__umul64hi(r, (uint64_t)avail));
+          u = et_u01(et_draw(key, (uint32_t)(dc + 2 * lane + 1)));
+        }
+        const uint32_t same = __match_any_sync(0xffffffffu, pick);
+        if (lane < nb && lane == __ffs(same) - 1) f = pick;
+        __syncwarp();
+        if (f >= 0) atomicOr(&s_taken[f >> 5], 1u << (f & 31));
+        dc += 64;
+      }
+      const bool act = f >= 0;
+      // ---- gather the node's samples of this lane's feature; min / max / hasMissing (pkg:34-54)
+      const double *col = p.X + (int64_t)(act ? f : 0) * p.ld;
+      double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;
+      bool has_nan = false;
+#pragma unroll 4
+      for (int j = 0; j < n; j++) {
+        const int32_t rj = __shfl_sync(0xffffffffu, row, j);
+        const double x = act ? __ldg(col + rj) : 0.0;
+        s_x[j * 32 + lane] = x;
+        if (x < mn) mn = x;
+        if (x > mx) mx = x;
+        has_nan |= (x != x);
+      }
+      const bool is_const = act && (mx <= mn) && !has_nan;  // pkg:236
+      const double cut = ET_ADD(mn, ET_MUL(ET_SUB(mx, mn), u));  // pkg:240
+      uint32_t lt = 0, nn = 0;
+      for (int j = 0; j < n; j++) {
+        const double x = s_x[j * 32 + lane];
+        lt |= (uint32_t)(x < cut) << j;
+        nn |= (uint32_t)(x != x) << j;
+      }
+      // ---- exact score of this lane's candidate (pkg:250-275)
+      double s = NAN;
+      bool mil = false;
+      if (act && !is_const) {
+        double sn, sl = NAN;
+        if (TASK == TASK_CLS) {
+          sn = gini_score_bits(lt, s_cm, C, n, total);
+          if (has_nan) sl = gini_score_bits(lt | nn, s_cm, C, n, total);
+        } else if (TASK == TASK_REG) {
+          sn = var_reduction_bits(lt, s_y, n, total);
+          if (has_nan) sl = var_reduction_bits(lt | nn, s_y, n, total);
+        } else {
+          sn = gini_score_w_bits(lt, s_cm, s_y, C, n, total, nsum);
+          if (has_nan) sl = gini_score_w_bits(lt | nn, s_cm, s_y, C, n, total, nsum);
+        }
+        mil = !(sl != sl) && (sl > sn || (sn != sn));
+        s = mil ? sl : sn;
+      }
+      // ---- consume the batch in draw (lane) order
+      const bool is_nan = act && !is_const && (s != s);
+      const bool counted = act && !is_const && !is_nan;
+      const uint32_t m_act = __ballot_sync(0xffffffffu, act);
+      const uint32_t m_const = __ballot_sync(0xffffffffu, is_const);
+      const uint32_t m_nan = __ballot_sync(0xffffffffu, is_nan);
+      const uint32_t m_cnt = __ballot_sync(0xffffffffu, counted);
+      if (p.replay) {
+        const bool bad = act && ((is_const && expect != 1) || (is_nan && expect != 3) || (counted && expect != 2));
+        st_mismatch += __popc(__ballot_sync(0xffffffffu, bad));
+      }
+      double bs = counted ? s : -INFINITY;
+      int bl = counted ? lane : 64;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+        const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+        if (os > bs || (os == bs && ol < bl)) {
+          bs = os;
+          bl = ol;
+        }
+      }
+      if (bl < 32 && bs > best_score) {  // strict >: the first best wins (pkg:277)
+        best_score = bs;
+        best_feature = __shfl_sync(0xffffffffu, f, bl);
+        best_cut = __shfl_sync(0xffffffffu, cut, bl);
+        best_mil = __shfl_sync(0xffffffffu, (int)mil, bl);
+        best_mask = __shfl_sync(0xffffffffu, mil ? (lt | nn) : lt, bl) & nmask;
+      }
+      if (!p.replay && (is_const || is_nan)) atomicOr(&s_const[f >> 5], 1u << (f & 31));
+      visited += __popc(m_cnt);
+      nconst += __popc(m_const) + __popc(m_nan);
+      st_draws += __popc(m_act);
+      st_const += __popc(m_const);
+      st_scored += __popc(m_cnt) + __popc(m_nan);
+      __syncwarp();
+    }
+  }
+
+  // ---------------- finalize ----------------
+  const bool make_leaf = leaf || best_feature < 0;
+  if (lane == 0) {
+    if (!leaf) {
+      atomicAdd(&p.cnt->st[ST_SROWS], (unsigned long long)n);
+      atomicAdd(&p.cnt->st[ST_VMM], (unsigned long long)n * st_draws);
+      atomicAdd(&p.cnt->st[ST_VSC], (unsigned long long)n * st_scored);
+      atomicAdd(&p.cnt->st[ST_DRAWS], st_draws);
+      atomicAdd(&p.cnt->st[ST_CONST], st_const);
+      atomicAdd(&p.cnt->st[ST_SCORED], st_scored);
+    }
+    if (p.replay) {
+      const bool trace_split = tn >= 0 && p.tr.left[tn] >= 0;
+      if (trace_split == make_leaf) st_mismatch++;
+      if (st_mismatch) atomicAdd(&p.cnt->st[ST_MISMATCH], st_mismatch);
+    }
+  }
+  if (make_leaf) {
+    int32_t ls = 0;
+    if (lane == 0) {
+      ls = atomicAdd(&p.cnt->n_leaves, 1);
+      p.o.feat[node] = -1;
+      p.o.child[node] = ls;
+      p.o.cut[node] = NAN;
+      p.o.tree[node] = tree;
+    }
+    ls = __shfl_sync(0xffffffffu, ls, 0);
+    double *lv = p.o.leaf_vals + (int64_t)ls * lw;
+    if (TASK == TASK_CLS) {
+      const double inv = ET_DIV(1.0, (double)n);
+      for (int c = lane; c < C; c += 32) lv[c] = et_repeat_add(inv, s_hnode[c]);
+    } else if (TASK == TASK_CLSW) {
+      for (int c = lane; c < C; c += 32) lv[c] = s_dist[c];
+    } else {
+      if (lane == 0) lv[0] = leaf_mean;
+    }
+    return;
+  }
+  const int32_t nl = __popc(best_mask);
+  int32_t slot = 0;
+  if (lane == 0) {
+    slot = atomicAdd(&p.cnt->next_f, 2);
+    const int32_t cl = p.node_base_next + slot;
+    p.o.feat[node] = best_feature | (best_mil ? ET_MIL_BIT : 0);
+    p.o.child[node] = cl;
+    p.o.cut[node] = best_cut;
+    p.o.tree[node] = tree;
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+      const int32_t s2 = slot + side;
+      p.nxt.tree[s2] = tree;
+      p.nxt.begin[s2] = side ? b + nl : b;
+      p.nxt.end[s2] = side ? e : b + nl;
+      p.nxt.node[s2] = cl + side;
+      p.nxt.depth[s2] = (TASK == TASK_REG && side) ? depth : depth + 1;
+      p.nxt.key[s2] = et_child_key(key, side);
+      int64_t tc = -1;
+      if (p.replay && tn >= 0) tc = side ? p.tr.right[tn] : p.tr.left[tn];
+      p.nxt.trace[s2] = tc;
+      p.q_nxt[0][atomicAdd(&p.cnt->q_count[0], 1)] = s2;  // children of a tiny node are tiny
+    }
+    atomicAdd(&p.cnt->st[ST_PROWS], (unsigned long long)n);
+  }
+  slot = __shfl_sync(0xffffffffu, slot, 0);
+  if (TASK == TASK_CLS) {
+    int32_t *hl = p.nxt.hist + (int64_t)slot * C, *hr = hl + C;
+    for (int c = lane; c < C; c += 32) {
+      const int32_t a = __popc(s_cm[c] & best_mask);
+      hl[c] = a;
+      hr[c] = s_hnode[c] - a;
+    }
+  }
+  if (!p.replay) {
+    uint32_t *ml = p.nxt.mask + (int64_t)slot * W, *mr = ml + W;
+    for (int w = lane; w < W; w += 32) {
+      const uint32_t v = s_const[w];
+      ml[w] = v;
+      mr[w] = v;
+    }
+  }
+  // the winner's side bitmask is the stable partition (pkg:1024-1039)
+  if (has) {
+    const bool left = (best_mask >> lane) & 1u;
+    const uint32_t below = (1u << lane) - 1u;
+    const int32_t dst = left ? b + __popc(best_mask & below) : b + nl + __popc(~best_mask & nmask & below);
+    p.idx_dst[base + dst] = row;
+    if (TASK == TASK_REG) {
+      p.yr_dst[base + dst] = yv;
+    } else {
+      p.yc_dst[base + dst] = cls;
+      if (TASK == TASK_CLSW) p.w_dst[base + dst] = wv;
     }
   }
 }
@@ -968,7 +1437,7 @@ struct PoolBufs {
 
 // Device buffers that survive across builds on one context (no cudaMalloc in the steady state).
 struct Workspace {
-  DevBuf<int32_t> idx[2], yc[2], q[2][2], size, nleaf, pos, lpos;
+  DevBuf<int32_t> idx[2], yc[2], q[2][NQ], size, nleaf, pos, lpos;
   DevBuf<double> yr[2], ws[2];
   FrontierBufs fr[2];
   PoolBufs pool;
@@ -998,7 +1467,7 @@ struct PhaseTimer {
   }
   void report() {
     if (!on) return;
-    static const char *names[] = {"alloc", "init", "node_warp", "node_cta", "sync", "preorder", "final", "other"};
+    static const char *names[] = {"alloc", "init", "node_warp", "node_cta", "sync", "preorder", "final", "node_tiny"};
     fprintf(stderr, "[etgpu timing ms]");
     for (int i = 0; i < 8; i++) fprintf(stderr, " %s=%.1f", names[i], acc[i]);
     fprintf(stderr, "\n");
@@ -1036,9 +1505,19 @@ struct EventTimer {
 };
 
 template <int TASK>
-void launch_level(et_ctx *ctx, const P &p, int32_t q0, int32_t q1, size_t smem_warp, size_t smem_cta, PhaseTimer &pt,
-                  EventTimer &et) {
+void launch_level(et_ctx *ctx, const P &p, const int32_t *qn, size_t smem_warp, size_t smem_cta, size_t smem_tiny,
+                  PhaseTimer &pt, EventTimer &et) {
   cudaStream_t st = ctx->stream;
+  const int32_t q0 = qn[1], q1 = qn[2];
+  if (qn[0] > 0) {
+    pt.start();
+    int e0 = et.rec(st);
+    k_node_tiny<TASK><<<(unsigned)ceil_div(qn[0], TINY_WARPS), 32 * TINY_WARPS, smem_tiny * TINY_WARPS, st>>>(p, qn[0]);
+    int e1 = et.rec(st);
+    et.spans[0].push_back({e0, e1});
+    ctx->launches++;
+    pt.stop(7);
+  }
   if (q0 > 0) {
     pt.start();
     int e0 = et.rec(st);
@@ -1060,7 +1539,8 @@ void launch_level(et_ctx *ctx, const P &p, int32_t q0, int32_t q1, size_t smem_w
 }
 
 template <int TASK>
-void set_smem_attr(size_t smem_warp_total, size_t smem_cta) {
+void set_smem_attr(size_t smem_warp_total, size_t smem_cta, size_t smem_tiny_total) {
+  CUDA_CHECK(cudaFuncSetAttribute(k_node_tiny<TASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tiny_total));
   CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_warp_total));
   CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, CTA_TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
 }
@@ -1097,12 +1577,15 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
   const Lay lay_w = make_lay(task, true, C, NB, W, replay), lay_c = make_lay(task, false, C, NB, W, replay);
   if ((size_t)lay_w.bytes * WARPS_PER_CTA > 200 * 1024 || (size_t)lay_c.bytes > 200 * 1024)
     ET_FAIL(ET_EUNSUPPORTED, "numClasses=%d / %d features need more shared memory per node than one SM has", C, d);
+  const size_t tiny_smem = (size_t)tiny_smem_bytes(task, C, W, replay);
+  if (tiny_smem * TINY_WARPS > 200 * 1024)
+    ET_FAIL(ET_EUNSUPPORTED, "numClasses=%d / %d features need more shared memory per node than one SM has", C, d);
   if (task == TASK_CLS)
-    set_smem_attr<TASK_CLS>((size_t)lay_w.bytes * WARPS_PER_CTA, (size_t)lay_c.bytes);
+    set_smem_attr<TASK_CLS>((size_t)lay_w.bytes * WARPS_PER_CTA, (size_t)lay_c.bytes, tiny_smem * TINY_WARPS);
   else if (task == TASK_CLSW)
-    set_smem_attr<TASK_CLSW>((size_t)lay_w.bytes * WARPS_PER_CTA, (size_t)lay_c.bytes);
+    set_smem_attr<TASK_CLSW>((size_t)lay_w.bytes * WARPS_PER_CTA, (size_t)lay_c.bytes, tiny_smem * TINY_WARPS);
   else
-    set_smem_attr<TASK_REG>((size_t)lay_w.bytes * WARPS_PER_CTA, (size_t)lay_c.bytes);
+    set_smem_attr<TASK_REG>((size_t)lay_w.bytes * WARPS_PER_CTA, (size_t)lay_c.bytes, tiny_smem * TINY_WARPS);
 
   cudaEvent_t ev0, ev1;
   CUDA_CHECK(cudaEventCreate(&ev0));
@@ -1218,7 +1701,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       int srcb = 0, cl = 0;
       int32_t F = Bt;
       ws.fr[0].ensure((size_t)F, C, W, task == TASK_CLS, !replay);
-      for (int q = 0; q < 2; q++) ws.q[0][q].ensure((size_t)F, 1.5);
+      for (int q = 0; q < NQ; q++) ws.q[0][q].ensure((size_t)F, 1.5);
       pt.stop(0);
       pt.start();
       {
@@ -1230,8 +1713,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
         ctx->launches++;
       }
       p.cur = ws.fr[0].view();
-      p.q_cur[0] = ws.q[0][0].p;
-      p.q_cur[1] = ws.q[0][1].p;
+      for (int q = 0; q < NQ; q++) p.q_cur[q] = ws.q[0][q].p;
       uint64_t *d_keys = upload_tmp(tree_keys.data() + t0, (size_t)Bt, st);
       int64_t *d_troots = replay ? upload_tmp(trace_roots.data() + t0, (size_t)Bt, st) : nullptr;
       CUDA_CHECK(cudaMemsetAsync(ws.cnt.p, 0, sizeof(Counters), st));
@@ -1244,17 +1726,18 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
 
       int64_t n_nodes = Bt, n_leaves = 0;
       std::vector<int32_t> level_start{0};
-      int32_t q0 = n <= NW_MAX ? Bt : 0, q1 = Bt - q0;
+      int32_t qn[NQ] = {0, 0, 0};
+      qn[size_class(n)] = Bt;
       Counters hc;
       memset(&hc, 0, sizeof(hc));
       while (F > 0) {
         S.levels++;
         pt.start();
         ws.fr[cl ^ 1].ensure((size_t)F * 2, C, W, task == TASK_CLS, !replay);
-        for (int q = 0; q < 2; q++) ws.q[cl ^ 1][q].ensure((size_t)F * 2, 1.5);
+        for (int q = 0; q < NQ; q++) ws.q[cl ^ 1][q].ensure((size_t)F * 2, 1.5);
         ws.pool.grow((size_t)(n_nodes + 2 * (int64_t)F), (size_t)n_nodes, (size_t)(n_leaves + F), (size_t)n_leaves, lw, st);
-        if (task != TASK_CLS && q1 > 0)
-          ws.scratch.ensure((size_t)NB * 2 * ((size_t)Bt * (size_t)n / 32 + (size_t)q1 + 1) + 64, 1.0);
+        if (task != TASK_CLS && qn[2] > 0)
+          ws.scratch.ensure((size_t)NB * 2 * ((size_t)Bt * (size_t)n / 32 + (size_t)qn[2] + 1) + 64, 1.0);
         pt.stop(0);
         p.idx_src = ws.idx[srcb].p;
         p.idx_dst = ws.idx[srcb ^ 1].p;
@@ -1266,19 +1749,19 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
         p.w_dst = ws.ws[srcb ^ 1].p;
         p.cur = ws.fr[cl].view();
         p.nxt = ws.fr[cl ^ 1].view();
-        p.q_cur[0] = ws.q[cl][0].p;
-        p.q_cur[1] = ws.q[cl][1].p;
-        p.q_nxt[0] = ws.q[cl ^ 1][0].p;
-        p.q_nxt[1] = ws.q[cl ^ 1][1].p;
+        for (int q = 0; q < NQ; q++) {
+          p.q_cur[q] = ws.q[cl][q].p;
+          p.q_nxt[q] = ws.q[cl ^ 1][q].p;
+        }
         p.o = ws.pool.view();
         p.scratch = ws.scratch.p;
         p.node_base_next = (int32_t)n_nodes;
         if (task == TASK_CLS)
-          launch_level<TASK_CLS>(ctx, p, q0, q1, (size_t)lay_w.bytes, (size_t)lay_c.bytes, pt, evt);
+          launch_level<TASK_CLS>(ctx, p, qn, (size_t)lay_w.bytes, (size_t)lay_c.bytes, tiny_smem, pt, evt);
         else if (task == TASK_CLSW)
-          launch_level<TASK_CLSW>(ctx, p, q0, q1, (size_t)lay_w.bytes, (size_t)lay_c.bytes, pt, evt);
+          launch_level<TASK_CLSW>(ctx, p, qn, (size_t)lay_w.bytes, (size_t)lay_c.bytes, tiny_smem, pt, evt);
         else
-          launch_level<TASK_REG>(ctx, p, q0, q1, (size_t)lay_w.bytes, (size_t)lay_c.bytes, pt, evt);
+          launch_level<TASK_REG>(ctx, p, qn, (size_t)lay_w.bytes, (size_t)lay_c.bytes, tiny_smem, pt, evt);
         pt.start();
         CUDA_CHECK(cudaMemcpyAsync(&hc, ws.cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         // the next level starts from clean per-level counters (leaf count and stats keep accumulating)
@@ -1293,8 +1776,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
         level_start.push_back((int32_t)n_nodes);
         n_nodes += nf;
         if (n_nodes > 0x7ffffff0) ET_FAIL(ET_EUNSUPPORTED, "batch exceeds 2^31 nodes; lower ETGPU_BATCH_TREES");
-        q0 = hc.q_count[0];
-        q1 = hc.q_count[1];
+        for (int q = 0; q < NQ; q++) qn[q] = hc.q_count[q];
         if (nf > 0) srcb ^= 1;
         F = nf;
         cl ^= 1;
