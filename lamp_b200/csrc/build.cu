@@ -38,7 +38,7 @@ enum { CF_CONST = 1, CF_NAN = 2, CF_MIL = 4 };
 enum { ST_VMM = 0, ST_VSC, ST_SROWS, ST_PROWS, ST_DRAWS, ST_CONST, ST_SCORED, ST_MISMATCH, ST_COUNT };
 
 constexpr int NT_MAX = 32;        // "tiny" nodes: one warp per node, one LANE per candidate
-constexpr int NW_MAX = 1024;      // nodes up to this many samples are owned by one warp (lanes on samples)
+constexpr int NW_MAX = 512;       // nodes up to this many samples are owned by one warp (lanes on samples)
 constexpr int BITS_W = NW_MAX / 32;
 constexpr int CTA_TEAM = 512;     // threads of the CTA that owns a larger node
 constexpr int WARPS_PER_CTA = 4;  // warp teams per CTA in the small-node kernel
@@ -77,9 +77,11 @@ struct Trace {
 
 // shared-memory layout of one team (identical on host and device)
 struct Lay {
-  int o_u, o_cut, o_score, o_dist, o_redd, o_wh;                                            // doubles
+  int o_u, o_cut, o_score, o_dist, o_redd, o_wh, o_xs, o_ys;                                // doubles
   int o_feat, o_flags, o_nleft, o_hnode, o_besthl, o_hist, o_redi, o_mask, o_bits, o_misc;  // int32
-  int hs;  // stride of one candidate's histogram row (odd: conflict-free per-candidate reads)
+  int o_rows, o_lab, o_cm;
+  int hs;      // stride of one candidate's histogram row (odd: conflict-free per-candidate reads)
+  int use_cm;  // warp teams: per-chunk class bitmasks fit in shared memory
   int bytes;
 };
 
@@ -98,6 +100,10 @@ __host__ __device__ inline Lay make_lay(int task, bool warp_team, int C, int NB,
   o += warp_team ? 0 : 64;
   L.o_wh = o;
   o += (task == TASK_CLSW) ? NB * 2 * C : 0;
+  L.o_xs = o;  // warp teams stage the node once: rows, labels / targets, and one candidate's values
+  o += warp_team ? NW_MAX : 0;
+  L.o_ys = o;
+  o += (warp_team && task != TASK_CLS) ? NW_MAX : 0;
   int oi = o * 2;  // switch to 4-byte units
   L.hs = (2 * C) | 1;
   L.o_feat = oi;
@@ -120,6 +126,13 @@ __host__ __device__ inline Lay make_lay(int task, bool warp_team, int C, int NB,
   oi += (task != TASK_CLS && warp_team) ? NB * 2 * BITS_W : 0;
   L.o_misc = oi;
   oi += 8;
+  L.o_rows = oi;
+  oi += warp_team ? NW_MAX : 0;
+  L.o_lab = oi;
+  oi += (warp_team && task != TASK_REG) ? NW_MAX : 0;
+  L.use_cm = (warp_team && task == TASK_CLS && BITS_W * C * 4 <= 8192) ? 1 : 0;
+  L.o_cm = oi;
+  oi += L.use_cm ? BITS_W * C : 0;
   L.bytes = ((oi + 3) / 4) * 16;
   return L;
 }
@@ -349,6 +362,32 @@ __device__ __forceinline__ int32_t rank_select_clear(const uint32_t *taken, int 
 // buildTree* (stop rules, pkg:993-994 / 813-814), split* (pkg:232-296 / 453-509: candidates
 // consumed in draw order, constants and NaN scores do not count toward k, strict `>` keeps the
 // first best), the child filters (pkg:1024-1039) and child creation.
+// position of the r-th set bit of z (r < popc(z))
+__device__ __forceinline__ int select_bit32(uint32_t z, int r) {
+  int pos = 0;
+#pragma unroll
+  for (int w = 16; w > 0; w >>= 1) {
+    const int c = __popc(z & ((1u << w) - 1u));
+    if (r >= c) {
+      r -= c;
+      z >>= w;
+      pos += w;
+    }
+  }
+  return pos;
+}
+
+__device__ __forceinline__ int32_t rank_select_clear_fast(const uint32_t *taken, int W, int32_t rank) {
+  for (int w = 0; w < W; w++) {
+    const uint32_t z = ~taken[w];
+    const int c = __popc(z);
+    if (rank < c) return w * 32 + select_bit32(z, rank);
+    rank -= c;
+  }
+  return -1;
+}
+
+
 template <int TASK, int TEAM>
 __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node(P p, int32_t qcount) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -365,12 +404,13 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
   double *smd = reinterpret_cast<double *>(sm);
   int32_t *smi = reinterpret_cast<int32_t *>(sm);
   double *s_u = smd + L.o_u, *s_cut = smd + L.o_cut, *s_score = smd + L.o_score, *s_dist = smd + L.o_dist;
-  double *s_redd = smd + L.o_redd, *s_wh = smd + L.o_wh;
+  double *s_redd = smd + L.o_redd, *s_wh = smd + L.o_wh, *s_xs = smd + L.o_xs, *s_ys = smd + L.o_ys;
   int32_t *s_feat = smi + L.o_feat, *s_flags = smi + L.o_flags, *s_nleft = smi + L.o_nleft;
   int32_t *s_hnode = smi + L.o_hnode, *s_besthl = smi + L.o_besthl, *s_hist = smi + L.o_hist, *s_redi = smi + L.o_redi;
   uint32_t *s_const = reinterpret_cast<uint32_t *>(smi + L.o_mask), *s_taken = s_const + W;
   uint32_t *s_bits = reinterpret_cast<uint32_t *>(smi + L.o_bits);
-  int32_t *s_misc = smi + L.o_misc;
+  int32_t *s_misc = smi + L.o_misc, *s_rows = smi + L.o_rows, *s_lab = smi + L.o_lab;
+  uint32_t *s_cm = reinterpret_cast<uint32_t *>(smi + L.o_cm);
 
   const int i = p.q_cur[WARP ? 1 : 2][q];
   const int32_t tree = p.cur.tree[i], b = p.cur.begin[i], e = p.cur.end[i], n = e - b;
@@ -378,8 +418,24 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
   const int64_t tn = p.cur.trace[i];
   const uint64_t key = p.cur.key[i];
   const int64_t base = (int64_t)tree * p.n;
-  const int32_t *idx = p.idx_src + base;
   const int lw = (TASK == TASK_REG) ? 1 : C;
+  const int nv = (n + 31) >> 5;
+
+  // A warp team stages its node once in shared memory (rows, labels, targets / weights); a CTA team
+  // streams the node's segment from HBM/L2.  rr/ll/yy/ww are indexed by position inside the node.
+  if (WARP) {
+    for (int j = lane; j < n; j += 32) {
+      s_rows[j] = p.idx_src[base + b + j];
+      if (TASK != TASK_REG) s_lab[j] = p.yc_src[base + b + j];
+      if (TASK == TASK_REG) s_ys[j] = p.yr_src[base + b + j];
+      if (TASK == TASK_CLSW) s_ys[j] = p.w_src[base + b + j];
+    }
+    __syncwarp();
+  }
+  const int32_t *rr = WARP ? s_rows : (p.idx_src + base + b);
+  const int32_t *ll = (TASK == TASK_REG) ? nullptr : (WARP ? s_lab : (p.yc_src + base + b));
+  const double *yy = (TASK != TASK_REG) ? nullptr : (WARP ? s_ys : (p.yr_src + base + b));
+  const double *ww = (TASK != TASK_CLSW) ? nullptr : (WARP ? s_ys : (p.w_src + base + b));
 
   // ---------------- stop rules + node totals ----------------
   bool leaf;
@@ -400,16 +456,15 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
       total = ET_SUB(1.0, s);
     }
   } else if (TASK == TASK_REG) {
-    const double *y = p.yr_src + base;
-    const double head = y[b];
+    const double head = yy[0];
     bool uni = true;
-    for (int32_t j = b + tid; j < e; j += TEAM) uni &= !(y[j] != head);
+    for (int32_t j = tid; j < n; j += TEAM) uni &= !(yy[j] != head);
     uni = team_all<TEAM>(uni, s_redi);
     leaf = (n < p.n_min) || (depth >= p.max_depth) || uni;  // pkg:813-814
     // mean2 (pkg:782) and varianceNoSplit (pkg:436-437), sequential in subset order
     if (tid == 0) {
       double sum = 0.0;
-      for (int32_t j = b; j < e; j++) sum = ET_ADD(sum, y[j]);
+      for (int32_t j = 0; j < n; j++) sum = ET_ADD(sum, yy[j]);
       const double dn = (double)n;
       const double mean = ET_DIV(sum, dn);
       double V = 0.0;
@@ -417,8 +472,8 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
         double var = 0.0;
         if (n > 1) {
           double qq = 0.0;
-          for (int32_t j = b; j < e; j++) {
-            double dl = ET_SUB(y[j], mean);
+          for (int32_t j = 0; j < n; j++) {
+            double dl = ET_SUB(yy[j], mean);
             qq = ET_ADD(qq, ET_MUL(dl, dl));
           }
           var = ET_DIV(qq, ET_SUB(dn, 1.0));
@@ -433,22 +488,20 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
     total = s_score[NB];
     team_sync<TEAM>();
   } else {
-    const int32_t *y = p.yc_src + base;
-    const double *w = p.w_src + base;
-    const int32_t head = y[b];
+    const int32_t head = ll[0];
     bool uni = true;
-    for (int32_t j = b + tid; j < e; j += TEAM) uni &= (y[j] == head);
+    for (int32_t j = tid; j < n; j += TEAM) uni &= (ll[j] == head);
     uni = team_all<TEAM>(uni, s_redi);
     leaf = (p.n_table < p.n_min) || (depth >= p.max_depth) || uni;
     // weighted distribution (pkg:913-927): sequential in subset order; also the leaf value
     if (tid == 0) {
       for (int c = 0; c < C; c++) s_dist[c] = 0.0;
       double s = 0.0;
-      for (int32_t j = b; j < e; j++) {
-        const double ww = w[j];
-        const int32_t cls = y[j];
-        s_dist[cls] = ET_ADD(s_dist[cls], ww);
-        s = ET_ADD(s, ww);
+      for (int32_t j = 0; j < n; j++) {
+        const double w1 = ww[j];
+        const int32_t cls = ll[j];
+        s_dist[cls] = ET_ADD(s_dist[cls], w1);
+        s = ET_ADD(s, w1);
       }
       double sq = 0.0;
       for (int c = 0; c < C; c++) {
@@ -489,8 +542,18 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
       for (int w = 0; w < W; w++) nc += __popc(s_const[w]);
       nconst = nc - (W * 32 - p.d);
     }
+    if (WARP && L.use_cm) {
+      // per 32-sample chunk, one bitmask per class: counting a side histogram becomes popc(ballot & mask)
+      for (int t = lane; t < nv * C; t += 32) s_cm[t] = 0u;
+      __syncwarp();
+      for (int v = 0; v < nv; v++) {
+        const int j = v * 32 + lane;
+        if (j < n) atomicOr(&s_cm[v * C + s_lab[j]], 1u << lane);
+      }
+      __syncwarp();
+    }
     uint32_t *g_bits = nullptr;  // CTA teams keep side bitmasks in global scratch
-    const int words = (n + 31) / 32;
+    const int words = nv;
     if (TASK != TASK_CLS && !WARP) {
       if (tid == 0) {
         unsigned long long off =
@@ -505,10 +568,19 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
     for (;;) {
       int32_t nb;
       const int32_t avail = p.d - nconst - visited;
-      if (p.replay)
+      if (p.replay) {
         nb = min(NB, tcnt - tpos);
-      else
-        nb = min(NB, min(p.k - visited, avail));
+      } else {
+        // draw what is still needed plus the constants expected among them (observed rate at this
+        // node); candidates past the k-th scored one are discarded unexamined, like the reference
+        // which stops drawing there
+        const int32_t need = min(p.k - visited, avail);
+        int32_t extra = 0;
+        if (need > 0 && st_draws > 0)
+          extra = (int32_t)(((long long)need * (long long)(st_draws - (unsigned long long)visited)) / max(visited, 1));
+        nb = min(NB, min(avail, need + extra));
+        if (need <= 0) nb = 0;
+      }
       if (nb <= 0) break;
       // ---- draw a batch of candidates (one lane per candidate)
       if (wit == 0) {
@@ -524,7 +596,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
           int32_t f = -1 - lane;
           if (lane < nb) {
             const uint64_t r = et_draw(key, (uint32_t)(dc + 2 * lane));
-            f = rank_select_clear(s_taken, W, (int32_t)__umul64hi(r, (uint64_t)avail));
+            f = rank_select_clear_fast(s_taken, W, (int32_t)__umul64hi(r, (uint64_t)avail));
           }
           const uint32_t same = __match_any_sync(0xffffffffu, f);
           const bool keep = (lane < nb) && (lane == __ffs(same) - 1);
@@ -551,11 +623,40 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
         const double *col = p.X + (int64_t)f * p.ld;
         double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;  // pkg:35-36
         int has_nan = 0;
-        for (int32_t j = b + tid; j < e; j += TEAM) {
-          const double x = __ldg(col + idx[j]);
-          if (x < mn) mn = x;
-          if (x > mx) mx = x;
-          has_nan |= (x != x);
+        if (WARP) {
+          // one gather per sample: the values are parked in shared memory for the second pass
+#pragma unroll 4
+          for (int v = 0; v < nv; v++) {
+            const int j = v * 32 + lane;
+            if (j < n) {
+              const double x = __ldg(col + s_rows[j]);
+              s_xs[j] = x;
+              if (x < mn) mn = x;
+              if (x > mx) mx = x;
+              has_nan |= (x != x);
+            }
+          }
+        } else {
+          for (int32_t j0 = 0; j0 < n; j0 += 4 * TEAM) {
+            int32_t r4[4];
+            double x4[4];
+#pragma unroll
+            for (int u2 = 0; u2 < 4; u2++) {
+              const int32_t j = j0 + u2 * TEAM + tid;
+              r4[u2] = (j < n) ? rr[j] : -1;
+            }
+#pragma unroll
+            for (int u2 = 0; u2 < 4; u2++) x4[u2] = (r4[u2] >= 0) ? __ldg(col + r4[u2]) : 0.0;
+#pragma unroll
+            for (int u2 = 0; u2 < 4; u2++) {
+              if (r4[u2] >= 0) {
+                const double x = x4[u2];
+                if (x < mn) mn = x;
+                if (x > mx) mx = x;
+                has_nan |= (x != x);
+              }
+            }
+          }
         }
         team_minmax<TEAM>(mn, mx, has_nan, s_redd, s_redi);
         if (mx <= mn && !has_nan) {  // pkg:236
@@ -568,18 +669,84 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
           if (has_nan) s_flags[c] |= CF_NAN;
         }
         if (TASK == TASK_CLS) {
-          const int32_t *y = p.yc_src + base;
           int32_t *hl = s_hist + c * L.hs, *hn = hl + C;
-          if (C <= 32) {
-            // lane == class: warp-aggregated counts
+          if (WARP && L.use_cm) {
+            int32_t al = 0, an = 0;  // lane == class (first 32 classes in registers)
+            for (int v = 0; v < nv; v++) {
+              const int j = v * 32 + lane;
+              const double x = (j < n) ? s_xs[j] : cut;
+              const uint32_t blt = __ballot_sync(0xffffffffu, x < cut);
+              const uint32_t bnan = has_nan ? __ballot_sync(0xffffffffu, x != x) : 0u;
+              if (C <= 32) {
+                if (lane < C) {
+                  const uint32_t m = s_cm[v * C + lane];
+                  al += __popc(blt & m);
+                  an += __popc(bnan & m);
+                }
+              } else {
+                for (int cc = lane; cc < C; cc += 32) {
+                  const uint32_t m = s_cm[v * C + cc];
+                  hl[cc] += __popc(blt & m);
+                  hn[cc] += __popc(bnan & m);
+                }
+              }
+            }
+            if (C <= 32 && lane < C) {
+              hl[lane] = al;
+              hn[lane] = an;
+            }
+          } else if (WARP) {
+            for (int j = lane; j < n; j += 32) {
+              const double x = s_xs[j];
+              if (x < cut)
+                atomicAdd(&hl[s_lab[j]], 1);
+              else if (x != x)
+                atomicAdd(&hn[s_lab[j]], 1);
+            }
+          } else if (C <= 16 && !has_nan) {
+            // per-thread packed 8-bit counters (one field per class), flushed before they can overflow
+            unsigned long long a0 = 0ull, a1 = 0ull;
+            int it = 0;
+            for (int32_t j0 = 0; j0 < n; j0 += 4 * TEAM) {
+              int32_t r4[4], c4[4];
+              double x4[4];
+#pragma unroll
+              for (int u2 = 0; u2 < 4; u2++) {
+                const int32_t j = j0 + u2 * TEAM + tid;
+                r4[u2] = (j < n) ? rr[j] : -1;
+                c4[u2] = (j < n) ? ll[j] : 0;
+              }
+#pragma unroll
+              for (int u2 = 0; u2 < 4; u2++) x4[u2] = (r4[u2] >= 0) ? __ldg(col + r4[u2]) : cut;
+#pragma unroll
+              for (int u2 = 0; u2 < 4; u2++) {
+                const unsigned long long inc = (x4[u2] < cut) ? 1ull : 0ull;
+                if (c4[u2] < 8)
+                  a0 += inc << (8 * c4[u2]);
+                else
+                  a1 += inc << (8 * (c4[u2] - 8));
+              }
+              it += 4;
+              if (it >= 252 || j0 + 4 * TEAM >= n) {  // uniform across the team
+                for (int cc = 0; cc < C; cc++) {
+                  const unsigned v = (unsigned)(((cc < 8) ? (a0 >> (8 * cc)) : (a1 >> (8 * (cc - 8)))) & 0xffull);
+                  const unsigned tot = __reduce_add_sync(0xffffffffu, v);
+                  if (lane == 0 && tot) atomicAdd(&hl[cc], (int32_t)tot);
+                }
+                a0 = 0ull;
+                a1 = 0ull;
+                it = 0;
+              }
+            }
+          } else if (C <= 32) {
             int32_t al = 0, an = 0;
-            for (int32_t j0 = b + wit * 32; j0 < e; j0 += TEAM) {
+            for (int32_t j0 = wit * 32; j0 < n; j0 += TEAM) {
               const int32_t j = j0 + lane;
               bool lt = false, isn = false;
               int32_t cls = -1;
-              if (j < e) {
-                const double x = __ldg(col + idx[j]);
-                cls = y[j];
+              if (j < n) {
+                const double x = __ldg(col + rr[j]);
+                cls = ll[j];
                 lt = x < cut;
                 isn = x != x;
               }
@@ -595,38 +762,33 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
               }
             }
             if (lane < C) {
-              if (WARP) {
-                hl[lane] = al;
-                hn[lane] = an;
-              } else {
-                if (al) atomicAdd(&hl[lane], al);
-                if (an) atomicAdd(&hn[lane], an);
-              }
+              if (al) atomicAdd(&hl[lane], al);
+              if (an) atomicAdd(&hn[lane], an);
             }
           } else {
-            for (int32_t j = b + tid; j < e; j += TEAM) {
-              const double x = __ldg(col + idx[j]);
+            for (int32_t j = tid; j < n; j += TEAM) {
+              const double x = __ldg(col + rr[j]);
               if (x < cut)
-                atomicAdd(&hl[y[j]], 1);
+                atomicAdd(&hl[ll[j]], 1);
               else if (x != x)
-                atomicAdd(&hn[y[j]], 1);
+                atomicAdd(&hn[ll[j]], 1);
             }
           }
         } else {
           uint32_t *mlt = WARP ? (s_bits + (size_t)c * 2 * BITS_W) : (g_bits + (size_t)c * 2 * words);
           uint32_t *mnan = mlt + (WARP ? BITS_W : words);
-          for (int32_t j0 = b + wit * 32; j0 < e; j0 += TEAM) {
+          for (int32_t j0 = wit * 32; j0 < n; j0 += TEAM) {
             const int32_t j = j0 + lane;
             bool lt = false, isn = false;
-            if (j < e) {
-              const double x = __ldg(col + idx[j]);
+            if (j < n) {
+              const double x = WARP ? s_xs[j] : __ldg(col + rr[j]);
               lt = x < cut;
               isn = x != x;
             }
             const uint32_t blt = __ballot_sync(0xffffffffu, lt), bnan = __ballot_sync(0xffffffffu, isn);
             if (lane == 0) {
-              mlt[(j0 - b) >> 5] = blt;
-              mnan[(j0 - b) >> 5] = bnan;
+              mlt[j0 >> 5] = blt;
+              mnan[j0 >> 5] = bnan;
             }
           }
         }
@@ -646,15 +808,12 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
           const uint32_t *mlt = WARP ? (s_bits + (size_t)c * 2 * BITS_W) : (g_bits + (size_t)c * 2 * words);
           const uint32_t *mnan = mlt + (WARP ? BITS_W : words);
           if (TASK == TASK_REG) {
-            const double *y = p.yr_src + base + b;
-            sn = var_reduction_seq(y, n, mlt, mnan, false, total, &nin_n);
-            if (has_nan) sl = var_reduction_seq(y, n, mlt, mnan, true, total, &nin_l);
+            sn = var_reduction_seq(yy, n, mlt, mnan, false, total, &nin_n);
+            if (has_nan) sl = var_reduction_seq(yy, n, mlt, mnan, true, total, &nin_l);
           } else {
-            const int32_t *y = p.yc_src + base + b;
-            const double *w = p.w_src + base + b;
             double *hin = s_wh + (size_t)c * 2 * C, *hout = hin + C;
-            sn = gini_score_w_seq(y, w, n, mlt, mnan, false, C, total, nsum, hin, hout, &nin_n);
-            if (has_nan) sl = gini_score_w_seq(y, w, n, mlt, mnan, true, C, total, nsum, hin, hout, &nin_l);
+            sn = gini_score_w_seq(ll, ww, n, mlt, mnan, false, C, total, nsum, hin, hout, &nin_n);
+            if (has_nan) sl = gini_score_w_seq(ll, ww, n, mlt, mnan, true, C, total, nsum, hin, hout, &nin_l);
           }
         }
         // pkg:272-275
@@ -667,12 +826,18 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
       // ---- consume the batch in draw order (every warp computes the same result; warp 0 of the
       //      team applies the side effects)
       {
-        const bool act = lane < nb && s_feat[lane] >= 0;
-        const int32_t fl = act ? s_flags[lane] : 0;
-        const bool is_const = act && (fl & CF_CONST);
-        const double s = (act && !is_const) ? s_score[lane] : NAN;
-        const bool is_nan = act && !is_const && (s != s);
-        const bool counted = act && !is_const && !is_nan;
+        const bool act0 = lane < nb && s_feat[lane] >= 0;
+        const int32_t fl = act0 ? s_flags[lane] : 0;
+        const bool const0 = act0 && (fl & CF_CONST);
+        const double s = (act0 && !const0) ? s_score[lane] : NAN;
+        const bool counted0 = act0 && !const0 && !(s != s);
+        // the reference stops drawing once k candidates have been scored: lanes past that point
+        // were never examined
+        const uint32_t m_cnt0 = __ballot_sync(0xffffffffu, counted0);
+        const bool act = act0 && (p.replay || __popc(m_cnt0 & ((1u << lane) - 1u)) < p.k - visited);
+        const bool is_const = act && const0;
+        const bool is_nan = act && !const0 && (s != s);
+        const bool counted = act && counted0;
         const uint32_t m_act = __ballot_sync(0xffffffffu, act);
         const uint32_t m_const = __ballot_sync(0xffffffffu, is_const);
         const uint32_t m_nan = __ballot_sync(0xffffffffu, is_nan);
@@ -807,13 +972,13 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
     const bool mil = best_mil != 0;
     int32_t lpos = b, rpos = b + best_nleft;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    for (int32_t j0 = b; j0 < e; j0 += TEAM) {
+    for (int32_t j0 = 0; j0 < n; j0 += TEAM) {
       const int32_t j = j0 + tid;
-      const bool valid = j < e;
+      const bool valid = j < n;
       int32_t r = 0;
       bool left = false;
       if (valid) {
-        r = idx[j];
+        r = rr[j];
         const double x = __ldg(col + r);
         left = (x < best_cut) || (mil && (x != x));
       }
@@ -844,10 +1009,10 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
         const int32_t dst = left ? lbase + __popc(bl & lt_mask) : rbase + __popc(br & lt_mask);
         p.idx_dst[base + dst] = r;
         if (TASK == TASK_REG) {
-          p.yr_dst[base + dst] = p.yr_src[base + j];
+          p.yr_dst[base + dst] = yy[j];
         } else {
-          p.yc_dst[base + dst] = p.yc_src[base + j];
-          if (TASK == TASK_CLSW) p.w_dst[base + dst] = p.w_src[base + j];
+          p.yc_dst[base + dst] = ll[j];
+          if (TASK == TASK_CLSW) p.w_dst[base + dst] = ww[j];
         }
       }
       lpos += ltot;
@@ -873,31 +1038,6 @@ __host__ __device__ inline int tiny_smem_bytes(int task, int C, int W, bool repl
   oi += (task == TASK_CLS) ? C : 0;          // s_hnode
   oi += replay ? 0 : 2 * W;                  // const / taken masks
   return ((oi + 3) / 4) * 16;
-}
-
-// position of the r-th set bit of z (r < popc(z))
-__device__ __forceinline__ int select_bit32(uint32_t z, int r) {
-  int pos = 0;
-#pragma unroll
-  for (int w = 16; w > 0; w >>= 1) {
-    const int c = __popc(z & ((1u << w) - 1u));
-    if (r >= c) {
-      r -= c;
-      z >>= w;
-      pos += w;
-    }
-  }
-  return pos;
-}
-
-__device__ __forceinline__ int32_t rank_select_clear_fast(const uint32_t *taken, int W, int32_t rank) {
-  for (int w = 0; w < W; w++) {
-    const uint32_t z = ~taken[w];
-    const int c = __popc(z);
-    if (rank < c) return w * 32 + select_bit32(z, rank);
-    rank -= c;
-  }
-  return -1;
 }
 
 // giniScore from a side bitmask (bit j = sample j goes left) and per-class sample bitmasks.
@@ -1121,7 +1261,7 @@ __global__ void __launch_bounds__(32 * TINY_WARPS) k_node_tiny(P p, int32_t qcou
       if (p.replay)
         nb = min(32, tcnt - tpos);
       else
-        nb = min(32, min(p.k - visited, avail));
+        nb = (p.k - visited > 0) ? min(32, avail) : 0;  // over-draw: unexamined extras are discarded below
       if (nb <= 0) break;
       // ---- draw: lane == candidate
       int32_t f = -1;
@@ -1147,21 +1287,21 @@ __global__ void __launch_bounds__(32 * TINY_WARPS) k_node_tiny(P p, int32_t qcou
         if (f >= 0) atomicOr(&s_taken[f >> 5], 1u << (f & 31));
         dc += 64;
       }
-      const bool act = f >= 0;
+      const bool act0 = f >= 0;
       // ---- gather the node's samples of this lane's feature; min / max / hasMissing (pkg:34-54)
-      const double *col = p.X + (int64_t)(act ? f : 0) * p.ld;
+      const double *col = p.X + (int64_t)(act0 ? f : 0) * p.ld;
       double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;
       bool has_nan = false;
 #pragma unroll 4
       for (int j = 0; j < n; j++) {
         const int32_t rj = __shfl_sync(0xffffffffu, row, j);
-        const double x = act ? __ldg(col + rj) : 0.0;
+        const double x = act0 ? __ldg(col + rj) : 0.0;
         s_x[j * 32 + lane] = x;
         if (x < mn) mn = x;
         if (x > mx) mx = x;
         has_nan |= (x != x);
       }
-      const bool is_const = act && (mx <= mn) && !has_nan;  // pkg:236
+      const bool const0 = act0 && (mx <= mn) && !has_nan;  // pkg:236
       const double cut = ET_ADD(mn, ET_MUL(ET_SUB(mx, mn), u));  // pkg:240
       uint32_t lt = 0, nn = 0;
       for (int j = 0; j < n; j++) {
@@ -1172,7 +1312,7 @@ __global__ void __launch_bounds__(32 * TINY_WARPS) k_node_tiny(P p, int32_t qcou
       // ---- exact score of this lane's candidate (pkg:250-275)
       double s = NAN;
       bool mil = false;
-      if (act && !is_const) {
+      if (act0 && !const0) {
         double sn, sl = NAN;
         if (TASK == TASK_CLS) {
           sn = gini_score_bits(lt, s_cm, C, n, total);
@@ -1187,9 +1327,14 @@ __global__ void __launch_bounds__(32 * TINY_WARPS) k_node_tiny(P p, int32_t qcou
         mil = !(sl != sl) && (sl > sn || (sn != sn));
         s = mil ? sl : sn;
       }
-      // ---- consume the batch in draw (lane) order
-      const bool is_nan = act && !is_const && (s != s);
-      const bool counted = act && !is_const && !is_nan;
+      // ---- consume the batch in draw (lane) order; the reference stops drawing once k candidates
+      //      have been scored, so lanes past that point were never examined
+      const bool counted0 = act0 && !const0 && !(s != s);
+      const uint32_t m_cnt0 = __ballot_sync(0xffffffffu, counted0);
+      const bool act = act0 && (p.replay || __popc(m_cnt0 & ((1u << lane) - 1u)) < p.k - visited);
+      const bool is_const = act && const0;
+      const bool is_nan = act && !const0 && (s != s);
+      const bool counted = act && counted0;
       const uint32_t m_act = __ballot_sync(0xffffffffu, act);
       const uint32_t m_const = __ballot_sync(0xffffffffu, is_const);
       const uint32_t m_nan = __ballot_sync(0xffffffffu, is_nan);
