@@ -351,22 +351,28 @@ def main():
     barrier()
     pred_e2e = n * world * args.steps / max_over_ranks(time.perf_counter() - t0)
 
-    # ---- roofline of the dominant kernel (split search: min/max + threshold score) -----------------
+    # ---- roofline of the dominant kernels: the node kernels (split search + stable partition fused) --------
+    # achieved = algorithmic bytes of the step (8*V_mm + (4+L)*S + 16*P, counters from et_stats)
+    #            / time inside the node kernels (CUDA events recorded around every node-kernel launch, et_stats)
     peak, peak_kind = measured_peak_hbm()
     L = 8 if cfg["task"] == "reg" else 4
-    alg_bytes_split = 8 * agg["v_mm"] + (4 + L) * agg["s_rows"]
-    alg_bytes_part = 16 * agg["p_rows"]
-    achieved = alg_bytes_split / (agg["gpu_ms_split"] / 1e3) / 1e9 if agg["gpu_ms_split"] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "split search (k_items*: min/max + threshold score)",
+    alg_bytes = 8 * agg["v_mm"] + (4 + L) * agg["s_rows"] + 16 * agg["p_rows"]
+    k_ms = agg["gpu_ms_split"]
+    achieved = alg_bytes / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per step from the last ncu --set full capture
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.config)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_node_tiny / k_node<32> / k_node<512> (split search + partition, one team per node)",
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
-                "algorithmic_bytes_per_step": alg_bytes_split / args.steps,
-                "kernel_ms_per_step": agg["gpu_ms_split"] / args.steps,
-                "share_of_step": agg["gpu_ms_split"] / (ms_build if world == 1 else max(ms_build, 1e-9)),
-                "partition": {"achieved": alg_bytes_part / (agg["gpu_ms_partition"] / 1e3) / 1e9
-                              if agg["gpu_ms_partition"] > 0 else 0.0,
-                              "kernel_ms_per_step": agg["gpu_ms_partition"] / args.steps},
-                "whole_build_achieved": (alg_bytes_split + alg_bytes_part) / (ms_build / 1e3) / 1e9}
+                "frac": achieved / peak, "traffic": traffic,
+                "algorithmic_bytes_per_step": alg_bytes / args.steps, "kernel_ms_per_step": k_ms / args.steps,
+                "share_of_step": k_ms / (ms_build * (1 if world == 1 else 1)),
+                "cta_nodes_ms_per_step": agg["gpu_ms_partition"] / args.steps,
+                "whole_build_achieved": alg_bytes / (ms_build / 1e3) / 1e9}
 
     launches = sum_over_ranks(agg["launches"])
     line = {

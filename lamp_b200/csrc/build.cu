@@ -79,7 +79,7 @@ struct Trace {
 struct Lay {
   int o_u, o_cut, o_score, o_dist, o_redd, o_wh, o_xs, o_ys;                                // doubles
   int o_feat, o_flags, o_nleft, o_hnode, o_besthl, o_hist, o_redi, o_mask, o_bits, o_misc;  // int32
-  int o_rows, o_lab, o_cm;
+  int o_rows, o_lab, o_cm, o_ord;
   int hs;      // stride of one candidate's histogram row (odd: conflict-free per-candidate reads)
   int use_cm;  // warp teams: per-chunk class bitmasks fit in shared memory
   int bytes;
@@ -126,6 +126,8 @@ __host__ __device__ inline Lay make_lay(int task, bool warp_team, int C, int NB,
   oi += (task != TASK_CLS && warp_team) ? NB * 2 * BITS_W : 0;
   L.o_misc = oi;
   oi += 8;
+  L.o_ord = oi;
+  oi += 32;
   L.o_rows = oi;
   oi += warp_team ? NW_MAX : 0;
   L.o_lab = oi;
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
   int32_t *s_hnode = smi + L.o_hnode, *s_besthl = smi + L.o_besthl, *s_hist = smi + L.o_hist, *s_redi = smi + L.o_redi;
   uint32_t *s_const = reinterpret_cast<uint32_t *>(smi + L.o_mask), *s_taken = s_const + W;
   uint32_t *s_bits = reinterpret_cast<uint32_t *>(smi + L.o_bits);
-  int32_t *s_misc = smi + L.o_misc, *s_rows = smi + L.o_rows, *s_lab = smi + L.o_lab;
+  int32_t *s_misc = smi + L.o_misc, *s_rows = smi + L.o_rows, *s_lab = smi + L.o_lab, *s_ord = smi + L.o_ord;
   uint32_t *s_cm = reinterpret_cast<uint32_t *>(smi + L.o_cm);
 
   const int i = p.q_cur[WARP ? 1 : 2][q];
@@ -613,13 +615,34 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
         tpos += nb;
       else
         dc += 2 * NB;
+      if (wit == 0) {
+        // Evaluate the batch in ascending feature order (results are consumed in draw order below):
+        // teams that run side by side then walk the column space together, so the handful of columns
+        // in flight chip-wide stays resident in L2 instead of every team streaming its own column.
+        __syncwarp();
+        uint32_t keyv = (lane < nb && s_feat[lane] >= 0) ? (((uint32_t)s_feat[lane] << 5) | (uint32_t)lane)
+                                                         : (0xffffffe0u | (uint32_t)lane);
+#pragma unroll
+        for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+          for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+            const uint32_t other = __shfl_xor_sync(0xffffffffu, keyv, j2);
+            const bool up = ((lane & k2) == 0);
+            const bool lower = ((lane & j2) == 0);
+            const uint32_t lo = min(keyv, other), hi = max(keyv, other);
+            keyv = (up == lower) ? lo : hi;
+          }
+        }
+        s_ord[lane] = (keyv >= 0xffffffe0u) ? -1 : (int32_t)(keyv & 31u);
+      }
       if (TASK == TASK_CLS)
         for (int t = tid; t < nb * L.hs; t += TEAM) s_hist[t] = 0;
       team_sync<TEAM>();
       // ---- phase 1: the whole team on the samples of one candidate at a time
-      for (int c = 0; c < nb; c++) {
+      for (int oi = 0; oi < 32; oi++) {
+        const int c = s_ord[oi];
+        if (c < 0) break;  // inactive slots sort last
         const int32_t f = s_feat[c];
-        if (f < 0) continue;
         const double *col = p.X + (int64_t)f * p.ld;
         double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;  // pkg:35-36
         int has_nan = 0;
