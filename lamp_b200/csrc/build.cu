@@ -40,11 +40,20 @@ enum { ST_VMM = 0, ST_VSC, ST_SROWS, ST_PROWS, ST_DRAWS, ST_CONST, ST_SCORED, ST
 constexpr int NT_MAX = 32;        // "tiny" nodes: one warp per node, one LANE per candidate
 constexpr int NW_MAX = 512;       // nodes up to this many samples are owned by one warp (lanes on samples)
 constexpr int BITS_W = NW_MAX / 32;
+constexpr int NM_MAX = 2048;      // nodes up to this many samples are owned by a 128-thread CTA
+constexpr int MID_TEAM = 128;
 constexpr int CTA_TEAM = 512;     // threads of the CTA that owns a larger node
+// CTA teams park one candidate's gathered values in shared memory when the node fits: the threshold pass
+// then needs no second gather (which would go to DRAM again at the top levels, where L2 is thrashed)
+// (8 B value + 4 B row + 1 B label per sample: 2048 -> 26 KB for the 128-thread team, 8192 -> 104 KB for the
+// 512-thread team, two of which fit one SM)
+__host__ __device__ constexpr int stage_cap(int team) { return team == 32 ? 0 : (team == MID_TEAM ? NM_MAX : 8192); }
 constexpr int WARPS_PER_CTA = 4;  // warp teams per CTA in the small-node kernel
 
-constexpr int NQ = 3;  // size classes: 0 tiny, 1 warp, 2 CTA
-__host__ __device__ inline int size_class(int64_t n) { return n <= NT_MAX ? 0 : (n <= NW_MAX ? 1 : 2); }
+constexpr int NQ = 4;  // size classes: 0 tiny, 1 warp, 2 CTA-128, 3 CTA-512
+__host__ __device__ inline int size_class(int64_t n) {
+  return n <= NT_MAX ? 0 : (n <= NW_MAX ? 1 : (n <= NM_MAX ? 2 : 3));
+}
 
 struct Counters {
   int32_t next_f;
@@ -85,7 +94,8 @@ struct Lay {
   int bytes;
 };
 
-__host__ __device__ inline Lay make_lay(int task, bool warp_team, int C, int NB, int W, bool replay) {
+__host__ __device__ inline Lay make_lay(int task, int team, int C, int NB, int W, bool replay) {
+  const bool warp_team = (team == 32);
   Lay L;
   int o = 0;  // in 8-byte units first
   L.o_u = o;
@@ -101,7 +111,7 @@ __host__ __device__ inline Lay make_lay(int task, bool warp_team, int C, int NB,
   L.o_wh = o;
   o += (task == TASK_CLSW) ? NB * 2 * C : 0;
   L.o_xs = o;  // warp teams stage the node once: rows, labels / targets, and one candidate's values
-  o += warp_team ? NW_MAX : 0;
+  o += warp_team ? NW_MAX : stage_cap(team);
   L.o_ys = o;
   o += (warp_team && task != TASK_CLS) ? NW_MAX : 0;
   int oi = o * 2;  // switch to 4-byte units
@@ -129,9 +139,9 @@ __host__ __device__ inline Lay make_lay(int task, bool warp_team, int C, int NB,
   L.o_ord = oi;
   oi += 32;
   L.o_rows = oi;
-  oi += warp_team ? NW_MAX : 0;
-  L.o_lab = oi;
-  oi += (warp_team && task != TASK_REG) ? NW_MAX : 0;
+  oi += warp_team ? NW_MAX : stage_cap(team);
+  L.o_lab = oi;  // warp teams: int32 labels; CTA teams: uint8 labels (used when C <= 256)
+  oi += (task != TASK_REG) ? (warp_team ? NW_MAX : stage_cap(team) / 4) : 0;
   L.use_cm = (warp_team && task == TASK_CLS && BITS_W * C * 4 <= 8192) ? 1 : 0;
   L.o_cm = oi;
   oi += L.use_cm ? BITS_W * C : 0;
@@ -391,7 +401,8 @@ __device__ __forceinline__ int32_t rank_select_clear_fast(const uint32_t *taken,
 
 
 template <int TASK, int TEAM>
-__global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node(P p, int32_t qcount) {
+__global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM, TEAM == 32 ? 5 : (TEAM == MID_TEAM ? 6 : 2))
+    k_node(P p, int32_t qcount) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool WARP = (TEAM == 32);
   const int tic = WARP ? (threadIdx.x >> 5) : 0;
@@ -401,7 +412,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
   const int lane = threadIdx.x & 31;
   const int wit = WARP ? 0 : (threadIdx.x >> 5);  // warp index inside the team
   const int C = p.C, NB = p.NB, W = p.W;
-  const Lay L = make_lay(TASK, WARP, C, NB, W, p.replay != 0);
+  const Lay L = make_lay(TASK, TEAM, C, NB, W, p.replay != 0);
   unsigned char *sm = smem_raw + (size_t)tic * L.bytes;
   double *smd = reinterpret_cast<double *>(sm);
   int32_t *smi = reinterpret_cast<int32_t *>(sm);
@@ -414,7 +425,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
   int32_t *s_misc = smi + L.o_misc, *s_rows = smi + L.o_rows, *s_lab = smi + L.o_lab, *s_ord = smi + L.o_ord;
   uint32_t *s_cm = reinterpret_cast<uint32_t *>(smi + L.o_cm);
 
-  const int i = p.q_cur[WARP ? 1 : 2][q];
+  const int i = p.q_cur[WARP ? 1 : (TEAM == MID_TEAM ? 2 : 3)][q];
   const int32_t tree = p.cur.tree[i], b = p.cur.begin[i], e = p.cur.end[i], n = e - b;
   const int32_t node = p.cur.node[i], depth = p.cur.depth[i];
   const int64_t tn = p.cur.trace[i];
@@ -422,6 +433,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
   const int64_t base = (int64_t)tree * p.n;
   const int lw = (TASK == TASK_REG) ? 1 : C;
   const int nv = (n + 31) >> 5;
+  const bool staged = !WARP && n <= stage_cap(TEAM);  // CTA team: one candidate's values fit in shared memory
 
   // A warp team stages its node once in shared memory (rows, labels, targets / weights); a CTA team
   // streams the node's segment from HBM/L2.  rr/ll/yy/ww are indexed by position inside the node.
@@ -434,8 +446,18 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
     }
     __syncwarp();
   }
-  const int32_t *rr = WARP ? s_rows : (p.idx_src + base + b);
+  const bool staged_lab = staged && TASK != TASK_REG && C <= 256;
+  uint8_t *s_lab8 = reinterpret_cast<uint8_t *>(s_lab);
+  if (staged) {
+    for (int j = tid; j < n; j += TEAM) {
+      s_rows[j] = p.idx_src[base + b + j];
+      if (staged_lab) s_lab8[j] = (uint8_t)p.yc_src[base + b + j];
+    }
+    __syncthreads();
+  }
+  const int32_t *rr = (WARP || staged) ? s_rows : (p.idx_src + base + b);
   const int32_t *ll = (TASK == TASK_REG) ? nullptr : (WARP ? s_lab : (p.yc_src + base + b));
+#define LAB(j) (staged_lab ? (int32_t)s_lab8[(j)] : ll[(j)])
   const double *yy = (TASK != TASK_REG) ? nullptr : (WARP ? s_ys : (p.yr_src + base + b));
   const double *ww = (TASK != TASK_CLSW) ? nullptr : (WARP ? s_ys : (p.w_src + base + b));
 
@@ -674,6 +696,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
             for (int u2 = 0; u2 < 4; u2++) {
               if (r4[u2] >= 0) {
                 const double x = x4[u2];
+                if (staged) s_xs[j0 + u2 * TEAM + tid] = x;
                 if (x < mn) mn = x;
                 if (x > mx) mx = x;
                 has_nan |= (x != x);
@@ -736,11 +759,12 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
 #pragma unroll
               for (int u2 = 0; u2 < 4; u2++) {
                 const int32_t j = j0 + u2 * TEAM + tid;
-                r4[u2] = (j < n) ? rr[j] : -1;
-                c4[u2] = (j < n) ? ll[j] : 0;
+                r4[u2] = (j < n) ? (staged ? j : rr[j]) : -1;
+                c4[u2] = (j < n) ? LAB(j) : 0;
               }
 #pragma unroll
-              for (int u2 = 0; u2 < 4; u2++) x4[u2] = (r4[u2] >= 0) ? __ldg(col + r4[u2]) : cut;
+              for (int u2 = 0; u2 < 4; u2++)
+                x4[u2] = (r4[u2] >= 0) ? (staged ? s_xs[r4[u2]] : __ldg(col + r4[u2])) : cut;
 #pragma unroll
               for (int u2 = 0; u2 < 4; u2++) {
                 const unsigned long long inc = (x4[u2] < cut) ? 1ull : 0ull;
@@ -768,8 +792,8 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
               bool lt = false, isn = false;
               int32_t cls = -1;
               if (j < n) {
-                const double x = __ldg(col + rr[j]);
-                cls = ll[j];
+                const double x = staged ? s_xs[j] : __ldg(col + rr[j]);
+                cls = LAB(j);
                 lt = x < cut;
                 isn = x != x;
               }
@@ -790,11 +814,11 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
             }
           } else {
             for (int32_t j = tid; j < n; j += TEAM) {
-              const double x = __ldg(col + rr[j]);
+              const double x = staged ? s_xs[j] : __ldg(col + rr[j]);
               if (x < cut)
-                atomicAdd(&hl[ll[j]], 1);
+                atomicAdd(&hl[LAB(j)], 1);
               else if (x != x)
-                atomicAdd(&hn[ll[j]], 1);
+                atomicAdd(&hn[LAB(j)], 1);
             }
           }
         } else {
@@ -804,7 +828,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
             const int32_t j = j0 + lane;
             bool lt = false, isn = false;
             if (j < n) {
-              const double x = WARP ? s_xs[j] : __ldg(col + rr[j]);
+              const double x = (WARP || staged) ? s_xs[j] : __ldg(col + rr[j]);
               lt = x < cut;
               isn = x != x;
             }
@@ -1034,7 +1058,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
         if (TASK == TASK_REG) {
           p.yr_dst[base + dst] = yy[j];
         } else {
-          p.yc_dst[base + dst] = ll[j];
+          p.yc_dst[base + dst] = LAB(j);
           if (TASK == TASK_CLSW) p.w_dst[base + dst] = ww[j];
         }
       }
@@ -1043,7 +1067,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM) k_node
     }
   }
 }
-
+#undef LAB
 
 // ---- tiny nodes (n <= 32): one warp per node, one LANE PER CANDIDATE ---------------------------
 // The node's rows sit in registers (lane j holds sample j); a batch of up to 32 candidate features
@@ -1635,7 +1659,7 @@ struct PhaseTimer {
   }
   void report() {
     if (!on) return;
-    static const char *names[] = {"alloc", "init", "node_warp", "node_cta", "sync", "preorder", "final", "node_tiny"};
+    static const char *names[] = {"alloc", "init", "node_warp", "node_cta", "sync", "preorder", "node_mid", "node_tiny"};
     fprintf(stderr, "[etgpu timing ms]");
     for (int i = 0; i < 8; i++) fprintf(stderr, " %s=%.1f", names[i], acc[i]);
     fprintf(stderr, "\n");
@@ -1673,10 +1697,19 @@ struct EventTimer {
 };
 
 template <int TASK>
-void launch_level(et_ctx *ctx, const P &p, const int32_t *qn, size_t smem_warp, size_t smem_cta, size_t smem_tiny,
-                  PhaseTimer &pt, EventTimer &et) {
+void launch_level(et_ctx *ctx, const P &p, const int32_t *qn, size_t smem_warp, size_t smem_mid, size_t smem_cta,
+                  size_t smem_tiny, PhaseTimer &pt, EventTimer &et) {
   cudaStream_t st = ctx->stream;
-  const int32_t q0 = qn[1], q1 = qn[2];
+  const int32_t q0 = qn[1], q1 = qn[3];
+  if (qn[2] > 0) {
+    pt.start();
+    int e0 = et.rec(st);
+    k_node<TASK, MID_TEAM><<<(unsigned)qn[2], MID_TEAM, smem_mid, st>>>(p, qn[2]);
+    int e1 = et.rec(st);
+    et.spans[1].push_back({e0, e1});
+    ctx->launches++;
+    pt.stop(6);
+  }
   if (qn[0] > 0) {
     pt.start();
     int e0 = et.rec(st);
@@ -1707,7 +1740,8 @@ void launch_level(et_ctx *ctx, const P &p, const int32_t *qn, size_t smem_warp, 
 }
 
 template <int TASK>
-void set_smem_attr(size_t smem_warp_total, size_t smem_cta, size_t smem_tiny_total) {
+void set_smem_attr(size_t smem_warp_total, size_t smem_mid, size_t smem_cta, size_t smem_tiny_total) {
+  CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, MID_TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mid));
   CUDA_CHECK(cudaFuncSetAttribute(k_node_tiny<TASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tiny_total));
   CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_warp_total));
   CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, CTA_TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
@@ -1738,22 +1772,26 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
 
   // candidates per batch: bounded by 32 lanes and by the team's shared memory
   int NB = 32;
-  const size_t smem_budget_warp = 40 * 1024, smem_budget_cta = 160 * 1024;
-  while (NB > 1 && ((size_t)make_lay(task, true, C, NB, W, replay).bytes > smem_budget_warp ||
-                    (size_t)make_lay(task, false, C, NB, W, replay).bytes > smem_budget_cta))
+  const size_t smem_budget_warp = 40 * 1024, smem_budget_cta = 110 * 1024;
+  while (NB > 1 && ((size_t)make_lay(task, 32, C, NB, W, replay).bytes > smem_budget_warp ||
+                    (size_t)make_lay(task, CTA_TEAM, C, NB, W, replay).bytes > smem_budget_cta))
     NB--;
-  const Lay lay_w = make_lay(task, true, C, NB, W, replay), lay_c = make_lay(task, false, C, NB, W, replay);
+  const Lay lay_w = make_lay(task, 32, C, NB, W, replay), lay_c = make_lay(task, CTA_TEAM, C, NB, W, replay);
+  const Lay lay_m = make_lay(task, MID_TEAM, C, NB, W, replay);
   if ((size_t)lay_w.bytes * WARPS_PER_CTA > 200 * 1024 || (size_t)lay_c.bytes > 200 * 1024)
     ET_FAIL(ET_EUNSUPPORTED, "numClasses=%d / %d features need more shared memory per node than one SM has", C, d);
   const size_t tiny_smem = (size_t)tiny_smem_bytes(task, C, W, replay);
   if (tiny_smem * TINY_WARPS > 200 * 1024)
     ET_FAIL(ET_EUNSUPPORTED, "numClasses=%d / %d features need more shared memory per node than one SM has", C, d);
   if (task == TASK_CLS)
-    set_smem_attr<TASK_CLS>((size_t)lay_w.bytes * WARPS_PER_CTA, (size_t)lay_c.bytes, tiny_smem * TINY_WARPS);
+    set_smem_attr<TASK_CLS>((size_t)lay_w.bytes * WARPS_PER_CTA, (size_t)lay_m.bytes, (size_t)lay_c.bytes,
+                            tiny_smem * TINY_WARPS);
   else if (task == TASK_CLSW)
-    set_smem_attr<TASK_CLSW>((size_t)lay_w.bytes * WARPS_PER_CTA, (size_t)lay_c.bytes, tiny_smem * TINY_WARPS);
+    set_smem_attr<TASK_CLSW>((size_t)lay_w.bytes * WARPS_PER_CTA, (size_t)lay_m.bytes, (size_t)lay_c.bytes,
+                             tiny_smem * TINY_WARPS);
   else
-    set_smem_attr<TASK_REG>((size_t)lay_w.bytes * WARPS_PER_CTA, (size_t)lay_c.bytes, tiny_smem * TINY_WARPS);
+    set_smem_attr<TASK_REG>((size_t)lay_w.bytes * WARPS_PER_CTA, (size_t)lay_m.bytes, (size_t)lay_c.bytes,
+                            tiny_smem * TINY_WARPS);
 
   cudaEvent_t ev0, ev1;
   CUDA_CHECK(cudaEventCreate(&ev0));
@@ -1894,7 +1932,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
 
       int64_t n_nodes = Bt, n_leaves = 0;
       std::vector<int32_t> level_start{0};
-      int32_t qn[NQ] = {0, 0, 0};
+      int32_t qn[NQ] = {0, 0, 0, 0};
       qn[size_class(n)] = Bt;
       Counters hc;
       memset(&hc, 0, sizeof(hc));
@@ -1904,8 +1942,8 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
         ws.fr[cl ^ 1].ensure((size_t)F * 2, C, W, task == TASK_CLS, !replay);
         for (int q = 0; q < NQ; q++) ws.q[cl ^ 1][q].ensure((size_t)F * 2, 1.5);
         ws.pool.grow((size_t)(n_nodes + 2 * (int64_t)F), (size_t)n_nodes, (size_t)(n_leaves + F), (size_t)n_leaves, lw, st);
-        if (task != TASK_CLS && qn[2] > 0)
-          ws.scratch.ensure((size_t)NB * 2 * ((size_t)Bt * (size_t)n / 32 + (size_t)qn[2] + 1) + 64, 1.0);
+        if (task != TASK_CLS && qn[2] + qn[3] > 0)
+          ws.scratch.ensure((size_t)NB * 2 * ((size_t)Bt * (size_t)n / 32 + (size_t)(qn[2] + qn[3]) + 1) + 64, 1.0);
         pt.stop(0);
         p.idx_src = ws.idx[srcb].p;
         p.idx_dst = ws.idx[srcb ^ 1].p;
@@ -1925,11 +1963,14 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
         p.scratch = ws.scratch.p;
         p.node_base_next = (int32_t)n_nodes;
         if (task == TASK_CLS)
-          launch_level<TASK_CLS>(ctx, p, qn, (size_t)lay_w.bytes, (size_t)lay_c.bytes, tiny_smem, pt, evt);
+          launch_level<TASK_CLS>(ctx, p, qn, (size_t)lay_w.bytes, (size_t)lay_m.bytes, (size_t)lay_c.bytes, tiny_smem, pt,
+                                  evt);
         else if (task == TASK_CLSW)
-          launch_level<TASK_CLSW>(ctx, p, qn, (size_t)lay_w.bytes, (size_t)lay_c.bytes, tiny_smem, pt, evt);
+          launch_level<TASK_CLSW>(ctx, p, qn, (size_t)lay_w.bytes, (size_t)lay_m.bytes, (size_t)lay_c.bytes, tiny_smem, pt,
+                                  evt);
         else
-          launch_level<TASK_REG>(ctx, p, qn, (size_t)lay_w.bytes, (size_t)lay_c.bytes, tiny_smem, pt, evt);
+          launch_level<TASK_REG>(ctx, p, qn, (size_t)lay_w.bytes, (size_t)lay_m.bytes, (size_t)lay_c.bytes, tiny_smem, pt,
+                                  evt);
         pt.start();
         CUDA_CHECK(cudaMemcpyAsync(&hc, ws.cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         // the next level starts from clean per-level counters (leaf count and stats keep accumulating)
@@ -2011,7 +2052,6 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       pt.stop(5);
     }
     // ---- the forest stays resident in HBM; batches are concatenated
-    pt.start();
     out->total_nodes = node_base;
     out->total_leaves = leaf_base;
     if (segs.size() == 1) {
@@ -2042,7 +2082,6 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
                                cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaEventRecord(ev1, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    pt.stop(6);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
     S.gpu_ms = ms;
