@@ -154,6 +154,15 @@ extern "C" int et_data_dense_colblock(et_ctx *ctx, et_data *D, const double *col
                                  (size_t)D->n * sizeof(double), (size_t)D->n * sizeof(double), (size_t)n_cols,
                                  cudaMemcpyHostToDevice, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (D->coded != 0) {  // the coded copy is rebuilt at the next build
+    if (D->c8) cudaFree(D->c8);
+    if (D->dict) cudaFree(D->dict);
+    if (D->coff) cudaFree(D->coff);
+    D->c8 = nullptr;
+    D->dict = nullptr;
+    D->coff = nullptr;
+    D->coded = 0;
+  }
   ET_API_END
 }
 
@@ -181,6 +190,7 @@ extern "C" int et_data_dense_rowmajor(et_ctx *ctx, const double *x, int64_t n, i
                                    ctx->stream));
         et_launch_transpose(ctx, stage, rows, d, D->x, D->ld, r0);
       }
+      et_data_encode(ctx, D);
       CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     } catch (...) {
       cudaFree(stage);
@@ -202,6 +212,7 @@ extern "C" int et_data_dense_rowmajor_device(et_ctx *ctx, const double *x_dev, i
   et_data *D = data_alloc(ctx, n, d);
   try {
     et_launch_transpose(ctx, x_dev, n, d, D->x, D->ld, 0);
+    et_data_encode(ctx, D);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   } catch (...) {
     et_data_free(D);
@@ -296,6 +307,9 @@ extern "C" void et_data_free(et_data *D) {
   if (!D) return;
   if (D->ctx) cudaSetDevice(D->ctx->device);
   if (D->x) cudaFree(D->x);
+  if (D->c8) cudaFree(D->c8);
+  if (D->dict) cudaFree(D->dict);
+  if (D->coff) cudaFree(D->coff);
   if (D->y_cls) cudaFree(D->y_cls);
   if (D->y_reg) cudaFree(D->y_reg);
   if (D->w) cudaFree(D->w);

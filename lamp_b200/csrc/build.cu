@@ -50,10 +50,11 @@ constexpr int CTA_TEAM = 512;     // threads of the CTA that owns a larger node
 __host__ __device__ constexpr int stage_cap(int team) { return team == 32 ? 0 : (team == MID_TEAM ? NM_MAX : 8192); }
 constexpr int WARPS_PER_CTA = 4;  // warp teams per CTA in the small-node kernel
 
-constexpr int NQ = 4;  // size classes: 0 tiny, 1 warp, 2 CTA-128, 3 CTA-512
-__host__ __device__ inline int size_class(int64_t n) {
-  return n <= NT_MAX ? 0 : (n <= NW_MAX ? 1 : (n <= NM_MAX ? 2 : 3));
-}
+// Size classes of the open nodes (upper bounds in P::cls_max; an empty class repeats its predecessor's bound):
+//   0, 1, 2  one warp per node, one lane per candidate (k_lane; classes 1, 2 only on byte-coded tables)
+//   2        (FP64 tables) one warp per node, lanes on samples (k_node<32>)
+//   3, 4     one CTA per node (k_node<128>, k_node<512>)
+constexpr int NQ = 5;
 
 struct Counters {
   int32_t next_f;
@@ -162,7 +163,18 @@ struct P {
   Counters *cnt;
   uint32_t *scratch;  // side bitmasks of CTA-owned nodes (TASK_CLSW / TASK_REG)
   int32_t node_base_next;
+  const uint8_t *C8;   // byte codes of the table, column-major [d][ldc] (encode.cu); null on FP64-only tables
+  int64_t ldc;
+  const double *dict;  // [d][256]
+  const uint8_t *coff; // [d] stored byte + coff = wide code (0 NaN, r + 1 for dict[r])
+  int32_t cls_max[NQ - 1];
 };
+
+__host__ __device__ inline int size_class(const P &p, int64_t n) {
+  int q = 0;
+  while (q < NQ - 1 && n > p.cls_max[q]) q++;
+  return q;
+}
 
 // ---- roots ----------------------------------------------------------------------------------
 __global__ void k_init_samples(int64_t n, int32_t B, int32_t *idx, const int32_t *y_cls, int32_t *yc,
@@ -197,7 +209,7 @@ __global__ void k_init_roots(P p, int32_t B, const uint64_t *tree_keys, const in
       p.cur.mask[(int64_t)t * p.W + w] = m;
     }
   }
-  p.q_cur[size_class(p.n)][t] = t;
+  p.q_cur[size_class(p, p.n)][t] = t;
 }
 
 // ---- team helpers ---------------------------------------------------------------------------
@@ -425,7 +437,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM, TEAM =
   int32_t *s_misc = smi + L.o_misc, *s_rows = smi + L.o_rows, *s_lab = smi + L.o_lab, *s_ord = smi + L.o_ord;
   uint32_t *s_cm = reinterpret_cast<uint32_t *>(smi + L.o_cm);
 
-  const int i = p.q_cur[WARP ? 1 : (TEAM == MID_TEAM ? 2 : 3)][q];
+  const int i = p.q_cur[WARP ? 2 : (TEAM == MID_TEAM ? 3 : 4)][q];
   const int32_t tree = p.cur.tree[i], b = p.cur.begin[i], e = p.cur.end[i], n = e - b;
   const int32_t node = p.cur.node[i], depth = p.cur.depth[i];
   const int64_t tn = p.cur.trace[i];
@@ -991,7 +1003,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM, TEAM =
       if (p.replay && tn >= 0) tc = side ? p.tr.right[tn] : p.tr.left[tn];
       p.nxt.trace[s2] = tc;
       const int32_t cn = side ? (n - nl) : nl;
-      const int qc = size_class(cn);
+      const int qc = size_class(p, cn);
       p.q_nxt[qc][atomicAdd(&p.cnt->q_count[qc], 1)] = s2;
     }
     atomicAdd(&p.cnt->st[ST_PROWS], (unsigned long long)n);
@@ -1069,36 +1081,48 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM, TEAM =
 }
 #undef LAB
 
-// ---- tiny nodes (n <= 32): one warp per node, one LANE PER CANDIDATE ---------------------------
-// The node's rows sit in registers (lane j holds sample j); a batch of up to 32 candidate features
-// is evaluated with every lane walking the node's samples for its own candidate: gather once into
-// shared memory, min/max, cutpoint, side bitmask over the samples, exact score from the bitmask.
-// No cross-lane reductions at all; the winner's bitmask IS the partition.
-constexpr int TINY_WARPS = 4;
+// ---- lane-per-candidate node kernel (n <= 32 * NW): one warp per node ---------------------------
+// Every lane owns ONE candidate feature of the batch and walks the node's samples for it: gather
+// once (parked in shared memory), min / max, cutpoint, side bitmask over the samples, exact score
+// from the bitmask.  No cross-lane reductions at all; the winner's bitmask IS the partition.
+// VT = double gathers FP64 values from X (NW == 1 only: 8 KB of parked values per warp);
+// VT = uint8_t gathers the order-preserving byte codes of encode.cu (wide code 0 = NaN, r + 1 = dict[r]):
+// min / max are integer, decoded through the dictionary, and `x < cut` is `code - 1 < thr` with
+// thr = number of dictionary entries below the cutpoint -- bit-identical decisions on 1/8 of the bytes,
+// and a node of up to 512 samples parks in 16 KB.
+constexpr int LANE_WARPS = 4;
 
-__host__ __device__ inline int tiny_smem_bytes(int task, int C, int W, bool replay) {
-  int o = NT_MAX * 32;                       // s_x   doubles [sample][lane]
-  o += (task == TASK_CLS) ? 0 : NT_MAX;      // s_y   doubles (regression target / weight)
-  o += (task == TASK_REG) ? 0 : C;           // s_dist doubles
-  int oi = o * 2;
-  oi += (task == TASK_REG) ? 0 : C;          // s_cm  class bitmasks over the samples
-  oi += (task == TASK_CLS) ? C : 0;          // s_hnode
-  oi += replay ? 0 : 2 * W;                  // const / taken masks
-  return ((oi + 3) / 4) * 16;
+__host__ __device__ inline int lane_smem_bytes(int task, int C, int W, bool replay, int NW, int vbytes) {
+  int o = 0;
+  o += (task == TASK_CLS) ? 0 : 32 * NW * 8;      // s_y    regression target / weight, by position
+  o += (task == TASK_REG) ? 0 : C * 8;            // s_dist
+  o += 32 * NW * 32 * vbytes;                     // s_x    parked values [position][lane]
+  o += (task == TASK_REG) ? 0 : C * NW * 4;       // s_cm   per class, bitmask over the positions
+  o += (task == TASK_REG) ? 0 : C * 4;            // s_hnode
+  o += replay ? 0 : 2 * W * 4;                    // const / taken masks
+  return ((o + 15) / 16) * 16;
 }
 
 // giniScore from a side bitmask (bit j = sample j goes left) and per-class sample bitmasks.
 // Classes absent from the node contribute exactly +0.0 to both sums and are skipped; an empty side
 // gives 0/0 = NaN exactly like the reference (pkg:1148-1157).
-__device__ __forceinline__ double gini_score_bits(uint32_t in_mask, const uint32_t *cm, int C, int32_t n, double G) {
-  const int32_t cin_i = __popc(in_mask);
+template <int NW>
+__device__ __forceinline__ double gini_score_bits(const uint32_t (&in)[NW], const uint32_t *cm, const int32_t *hnode,
+                                                  int C, int32_t n, int nw, double G) {
+  int32_t cin_i = 0;
+#pragma unroll
+  for (int w = 0; w < NW; w++) cin_i += __popc(in[w]);
   if (cin_i == 0 || cin_i == n) return NAN;
   const double cin = (double)cin_i, cout = (double)(n - cin_i), N = (double)n;
   double sin_ = 0.0, sout = 0.0;
   for (int c = 0; c < C; c++) {
-    const uint32_t m = cm[c];
-    if (m == 0) continue;
-    const int32_t hi = __popc(m & in_mask), ho = __popc(m) - hi;
+    const int32_t ht = hnode[c];
+    if (ht == 0) continue;
+    int32_t hi = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++)
+      if (w < nw) hi += __popc(cm[c * NW + w] & in[w]);
+    const int32_t ho = ht - hi;
     const double pi = ET_DIV((double)hi, cin), po = ET_DIV((double)ho, cout);
     sin_ = ET_ADD(sin_, ET_MUL(pi, pi));
     sout = ET_ADD(sout, ET_MUL(po, po));
@@ -1110,26 +1134,38 @@ __device__ __forceinline__ double gini_score_bits(uint32_t in_mask, const uint32
 // weighted giniScore (pkg:1132-1157): per-class and per-side sums in subset order.  Each of the
 // reference's accumulators only ever sees its own samples, so walking the samples class by class
 // (in subset order inside a class) performs the same additions in the same order.
-__device__ __forceinline__ double gini_score_w_bits(uint32_t in_mask, const uint32_t *cm, const double *w, int C,
-                                                   int32_t n, double G, double N) {
+template <int NW>
+__device__ __forceinline__ double gini_score_w_bits(const uint32_t (&in)[NW], const uint32_t *cm, const double *w,
+                                                    int C, int32_t n, int nw, double G, double N) {
   double cin = 0.0, cout = 0.0;
-  for (int j = 0; j < n; j++) {
-    if ((in_mask >> j) & 1u)
-      cin = ET_ADD(cin, w[j]);
-    else
-      cout = ET_ADD(cout, w[j]);
+#pragma unroll
+  for (int v = 0; v < NW; v++) {
+    if (v < nw) {
+      const int cnt = min(32, n - v * 32);
+      for (int j = 0; j < cnt; j++) {
+        if ((in[v] >> j) & 1u)
+          cin = ET_ADD(cin, w[v * 32 + j]);
+        else
+          cout = ET_ADD(cout, w[v * 32 + j]);
+      }
+    }
   }
   double sin_ = 0.0, sout = 0.0;
   for (int c = 0; c < C; c++) {
-    uint32_t m = cm[c];
     double hi = 0.0, ho = 0.0;
-    while (m) {
-      const int j = __ffs(m) - 1;
-      m &= m - 1;
-      if ((in_mask >> j) & 1u)
-        hi = ET_ADD(hi, w[j]);
-      else
-        ho = ET_ADD(ho, w[j]);
+#pragma unroll
+    for (int v = 0; v < NW; v++) {
+      if (v < nw) {
+        uint32_t m = cm[c * NW + v];
+        while (m) {
+          const int j = __ffs(m) - 1;
+          m &= m - 1;
+          if ((in[v] >> j) & 1u)
+            hi = ET_ADD(hi, w[v * 32 + j]);
+          else
+            ho = ET_ADD(ho, w[v * 32 + j]);
+        }
+      }
     }
     const double pi = ET_DIV(hi, cin), po = ET_DIV(ho, cout);
     sin_ = ET_ADD(sin_, ET_MUL(pi, pi));
@@ -1140,25 +1176,41 @@ __device__ __forceinline__ double gini_score_w_bits(uint32_t in_mask, const uint
 }
 
 // computeVarianceReduction (pkg:1196-1218) from a side bitmask, sequential in subset order
-__device__ __forceinline__ double var_reduction_bits(uint32_t in_mask, const double *y, int32_t n, double V) {
+template <int NW>
+__device__ __forceinline__ double var_reduction_bits(const uint32_t (&in)[NW], const double *y, int32_t n, int nw,
+                                                     double V) {
   double sin_ = 0.0, sout = 0.0;
-  for (int j = 0; j < n; j++) {
-    if ((in_mask >> j) & 1u)
-      sin_ = ET_ADD(sin_, y[j]);
-    else
-      sout = ET_ADD(sout, y[j]);
+  int32_t nin = 0;
+#pragma unroll
+  for (int v = 0; v < NW; v++) {
+    if (v < nw) {
+      nin += __popc(in[v]);
+      const int cnt = min(32, n - v * 32);
+      for (int j = 0; j < cnt; j++) {
+        if ((in[v] >> j) & 1u)
+          sin_ = ET_ADD(sin_, y[v * 32 + j]);
+        else
+          sout = ET_ADD(sout, y[v * 32 + j]);
+      }
+    }
   }
-  const int32_t nin = __popc(in_mask), nout = n - nin;
+  const int32_t nout = n - nin;
   const double dnin = (double)nin, dnout = (double)nout, dn = (double)n;
   const double min_ = ET_DIV(sin_, dnin), mout = ET_DIV(sout, dnout);
   double qin = 0.0, qout = 0.0;
-  for (int j = 0; j < n; j++) {
-    if ((in_mask >> j) & 1u) {
-      const double dl = ET_SUB(y[j], min_);
-      qin = ET_ADD(qin, ET_MUL(dl, dl));
-    } else {
-      const double dl = ET_SUB(y[j], mout);
-      qout = ET_ADD(qout, ET_MUL(dl, dl));
+#pragma unroll
+  for (int v = 0; v < NW; v++) {
+    if (v < nw) {
+      const int cnt = min(32, n - v * 32);
+      for (int j = 0; j < cnt; j++) {
+        if ((in[v] >> j) & 1u) {
+          const double dl = ET_SUB(y[v * 32 + j], min_);
+          qin = ET_ADD(qin, ET_MUL(dl, dl));
+        } else {
+          const double dl = ET_SUB(y[v * 32 + j], mout);
+          qout = ET_ADD(qout, ET_MUL(dl, dl));
+        }
+      }
     }
   }
   const double svin = nin < 1 ? NAN : (nin == 1 ? 0.0 : ET_DIV(qin, ET_SUB(dnin, 1.0)));
@@ -1170,61 +1222,79 @@ __device__ __forceinline__ double var_reduction_bits(uint32_t in_mask, const dou
   return ET_DIV(ET_SUB(ET_SUB(V, a), bq), V);
 }
 
-template <int TASK>
-__global__ void __launch_bounds__(32 * TINY_WARPS) k_node_tiny(P p, int32_t qcount) {
+template <int TASK, typename VT, int NW>
+__global__ void __launch_bounds__(32 * LANE_WARPS) k_lane(P p, int32_t qcount, int qi) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr bool CODED = (sizeof(VT) != 8);
+  constexpr uint32_t FULL = 0xffffffffu;
   const int tic = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = blockIdx.x * TINY_WARPS + tic;
+  const int q = blockIdx.x * LANE_WARPS + tic;
   if (q >= qcount) return;
   const int C = p.C, W = p.W;
-  unsigned char *sm = smem_raw + (size_t)tic * tiny_smem_bytes(TASK, C, W, p.replay != 0);
-  double *s_x = reinterpret_cast<double *>(sm);
-  double *s_y = s_x + NT_MAX * 32;
-  double *s_dist = s_y + ((TASK == TASK_CLS) ? 0 : NT_MAX);
-  uint32_t *s_cm = reinterpret_cast<uint32_t *>(s_dist + ((TASK == TASK_REG) ? 0 : C));
-  int32_t *s_hnode = reinterpret_cast<int32_t *>(s_cm + ((TASK == TASK_REG) ? 0 : C));
-  uint32_t *s_const = reinterpret_cast<uint32_t *>(s_hnode + ((TASK == TASK_CLS) ? C : 0)), *s_taken = s_const + W;
+  unsigned char *sm = smem_raw + (size_t)tic * lane_smem_bytes(TASK, C, W, p.replay != 0, NW, (int)sizeof(VT));
+  double *s_y = reinterpret_cast<double *>(sm);
+  double *s_dist = s_y + ((TASK == TASK_CLS) ? 0 : 32 * NW);
+  VT *s_x = reinterpret_cast<VT *>(s_dist + ((TASK == TASK_REG) ? 0 : C));
+  uint32_t *s_cm = reinterpret_cast<uint32_t *>(s_x + 32 * NW * 32);
+  int32_t *s_hnode = reinterpret_cast<int32_t *>(s_cm + ((TASK == TASK_REG) ? 0 : C * NW));
+  uint32_t *s_const = reinterpret_cast<uint32_t *>(s_hnode + ((TASK == TASK_REG) ? 0 : C)), *s_taken = s_const + W;
 
-  const int i = p.q_cur[0][q];
+  const int i = p.q_cur[qi][q];
   const int32_t tree = p.cur.tree[i], b = p.cur.begin[i], e = p.cur.end[i], n = e - b;
   const int32_t node = p.cur.node[i], depth = p.cur.depth[i];
   const int64_t tn = p.cur.trace[i];
   const uint64_t key = p.cur.key[i];
   const int64_t base = (int64_t)tree * p.n;
   const int lw = (TASK == TASK_REG) ? 1 : C;
-  const uint32_t nmask = (n >= 32) ? 0xffffffffu : ((1u << n) - 1u);
+  const int nw = (n + 31) >> 5;
+  const int32_t *idx = p.idx_src + base + b;
 
-  // the node's samples: lane j holds sample j
-  const bool has = lane < n;
-  const int32_t row = has ? p.idx_src[base + b + lane] : 0;
-  int32_t cls = -1;
-  double yv = 0.0, wv = 0.0;
+  // ---------------- the node's labels / targets (position j = w * 32 + lane) ----------------
   if (TASK != TASK_REG) {
-    if (has) cls = p.yc_src[base + b + lane];
-    for (int c = lane; c < C; c += 32) s_cm[c] = 0u;
+    for (int t = lane; t < C * NW; t += 32) s_cm[t] = 0u;
     __syncwarp();
-    if (has) atomicOr(&s_cm[cls], 1u << lane);
+    const int32_t *yc = p.yc_src + base + b;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+      if (w < nw) {
+        const int j = w * 32 + lane;
+        const bool has = j < n;
+        const int32_t cls = has ? yc[j] : -1;
+        const uint32_t grp = __match_any_sync(FULL, cls);
+        if (has && lane == __ffs(grp) - 1) s_cm[cls * NW + w] = grp;
+      }
+    }
   }
   if (TASK == TASK_REG) {
-    if (has) yv = p.yr_src[base + b + lane];
-    s_y[lane] = yv;
+    const double *yr = p.yr_src + base + b;
+    for (int j = lane; j < n; j += 32) s_y[j] = yr[j];
   }
   if (TASK == TASK_CLSW) {
-    if (has) wv = p.w_src[base + b + lane];
-    s_y[lane] = wv;
+    const double *wr = p.w_src + base + b;
+    for (int j = lane; j < n; j += 32) s_y[j] = wr[j];
   }
   __syncwarp();
 
   // ---------------- stop rules + node totals ----------------
   bool leaf;
   double total = 0.0, nsum = (double)n, leaf_mean = 0.0;
-  if (TASK == TASK_CLS) {
-    for (int c = lane; c < C; c += 32) s_hnode[c] = __popc(s_cm[c]);
-    const int32_t cls0 = __shfl_sync(0xffffffffu, cls, 0);  // (never inside a short-circuit: all lanes shuffle)
-    const bool pure = __all_sync(0xffffffffu, !has || cls == cls0);
-    leaf = (p.n_table < p.n_min) || (depth >= p.max_depth) || pure;
+  if (TASK != TASK_REG) {
+    bool pure_l = false;
+    for (int c = lane; c < C; c += 32) {
+      int32_t h = 0;
+#pragma unroll
+      for (int w = 0; w < NW; w++)
+        if (w < nw) h += __popc(s_cm[c * NW + w]);
+      s_hnode[c] = h;
+      pure_l |= (h == n);
+    }
+    const bool pure = __any_sync(FULL, pure_l);  // all targets in the subset equal (weights ignored)
+    leaf = (p.n_table < p.n_min) || (depth >= p.max_depth) || pure;  // pkg:993-994
     __syncwarp();
+  }
+  if (TASK == TASK_CLS) {
     if (!leaf) {
+      // giniImpurity with the reference's repeated `+= 1/s` distribution (pkg:905-911, 1160-1180)
       const double inv = ET_DIV(1.0, (double)n);
       for (int c = lane; c < C; c += 32) s_dist[c] = et_repeat_add(inv, s_hnode[c]);
       __syncwarp();
@@ -1233,9 +1303,12 @@ __global__ void __launch_bounds__(32 * TINY_WARPS) k_node_tiny(P p, int32_t qcou
       total = ET_SUB(1.0, s);
     }
   } else if (TASK == TASK_REG) {
-    const double head = __shfl_sync(0xffffffffu, yv, 0);
-    const bool uni = __all_sync(0xffffffffu, !has || !(yv != head));
-    leaf = (n < p.n_min) || (depth >= p.max_depth) || uni;
+    const double head = s_y[0];
+    bool uni_l = true;
+    for (int j = lane; j < n; j += 32) uni_l &= !(s_y[j] != head);
+    const bool uni = __all_sync(FULL, uni_l);
+    leaf = (n < p.n_min) || (depth >= p.max_depth) || uni;  // pkg:813-814
+    // mean2 (pkg:782) and varianceNoSplit (pkg:436-437), sequential in subset order
     double sum = 0.0;
     for (int j = 0; j < n; j++) sum = ET_ADD(sum, s_y[j]);
     const double dn = (double)n;
@@ -1253,19 +1326,21 @@ __global__ void __launch_bounds__(32 * TINY_WARPS) k_node_tiny(P p, int32_t qcou
       total = ET_DIV(ET_MUL(var, ET_SUB(dn, 1.0)), dn);
     }
   } else {
-    const int32_t cls0 = __shfl_sync(0xffffffffu, cls, 0);
-    const bool uni = __all_sync(0xffffffffu, !has || cls == cls0);
-    leaf = (p.n_table < p.n_min) || (depth >= p.max_depth) || uni;
     // weighted distribution (pkg:913-927): per-class sums and the total, each in subset order
     double s = 0.0;
     for (int j = 0; j < n; j++) s = ET_ADD(s, s_y[j]);
     for (int c = lane; c < C; c += 32) {
-      uint32_t m = s_cm[c];
       double a = 0.0;
-      while (m) {
-        const int j = __ffs(m) - 1;
-        m &= m - 1;
-        a = ET_ADD(a, s_y[j]);
+#pragma unroll
+      for (int w = 0; w < NW; w++) {
+        if (w < nw) {
+          uint32_t m = s_cm[c * NW + w];
+          while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            a = ET_ADD(a, s_y[w * 32 + j]);
+          }
+        }
       }
       s_dist[c] = ET_DIV(a, s);
     }
@@ -1278,7 +1353,9 @@ __global__ void __launch_bounds__(32 * TINY_WARPS) k_node_tiny(P p, int32_t qcou
 
   // ---------------- split search ----------------
   int32_t visited = 0, nconst = 0, best_feature = -1, best_mil = 0;
-  uint32_t best_mask = 0;
+  uint32_t best_mask[NW];
+#pragma unroll
+  for (int w = 0; w < NW; w++) best_mask[w] = 0u;
   double best_score = -INFINITY, best_cut = NAN;
   unsigned long long st_draws = 0, st_const = 0, st_scored = 0, st_mismatch = 0;
   if (!leaf) {
@@ -1298,17 +1375,21 @@ __global__ void __launch_bounds__(32 * TINY_WARPS) k_node_tiny(P p, int32_t qcou
         nc += __popc(m);
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) nc += __shfl_xor_sync(0xffffffffu, nc, o);
+      for (int o = 16; o > 0; o >>= 1) nc += __shfl_xor_sync(FULL, nc, o);
       nconst = nc - (W * 32 - p.d);
       __syncwarp();
     }
     for (;;) {
       int32_t nb;
       const int32_t avail = p.d - nconst - visited;
-      if (p.replay)
+      if (p.replay) {
         nb = min(32, tcnt - tpos);
-      else
-        nb = (p.k - visited > 0) ? min(32, avail) : 0;  // over-draw: unexamined extras are discarded below
+      } else {
+        // over-draw (about half of the draws hit constants on sparse tables); candidates past the k-th
+        // scored one are discarded unexamined below, like the reference which stops drawing there
+        const int32_t need = min(p.k - visited, avail);
+        nb = (need > 0) ? min(32, min(avail, 2 * need + 4)) : 0;
+      }
       if (nb <= 0) break;
       // ---- draw: lane == candidate
       int32_t f = -1;
@@ -1328,74 +1409,137 @@ __global__ void __launch_bounds__(32 * TINY_WARPS) k_node_tiny(P p, int32_t qcou
           pick = rank_select_clear_fast(s_taken, W, (int32_t)__umul64hi(r, (uint64_t)avail));
           u = et_u01(et_draw(key, (uint32_t)(dc + 2 * lane + 1)));
         }
-        const uint32_t same = __match_any_sync(0xffffffffu, pick);
+        const uint32_t same = __match_any_sync(FULL, pick);
         if (lane < nb && lane == __ffs(same) - 1) f = pick;
         __syncwarp();
         if (f >= 0) atomicOr(&s_taken[f >> 5], 1u << (f & 31));
         dc += 64;
       }
       const bool act0 = f >= 0;
-      // ---- gather the node's samples of this lane's feature; min / max / hasMissing (pkg:34-54)
-      const double *col = p.X + (int64_t)(act0 ? f : 0) * p.ld;
-      double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;
+      // ---- pass 1: gather the node's samples of this lane's feature; min / max / hasMissing (pkg:34-54)
+      const VT *col = CODED ? reinterpret_cast<const VT *>(p.C8) + (int64_t)(act0 ? f : 0) * p.ldc
+                            : reinterpret_cast<const VT *>(p.X) + (int64_t)(act0 ? f : 0) * p.ld;
+      double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;  // pkg:35-36
       bool has_nan = false;
-#pragma unroll 4
-      for (int j = 0; j < n; j++) {
-        const int32_t rj = __shfl_sync(0xffffffffu, row, j);
-        const double x = act0 ? __ldg(col + rj) : 0.0;
-        s_x[j * 32 + lane] = x;
-        if (x < mn) mn = x;
-        if (x > mx) mx = x;
-        has_nan |= (x != x);
+      uint32_t mnc = 0xffffffffu, mxc = 0u, mnraw = 0xffffffffu;
+      const uint32_t coff = (CODED && act0) ? (uint32_t)__ldg(p.coff + f) : 0u;
+      for (int w = 0; w < nw; w++) {
+        const int j0 = w << 5, cnt = min(32, n - j0);
+        const int32_t row = (lane < cnt) ? idx[j0 + lane] : 0;
+#pragma unroll 8
+        for (int jj = 0; jj < cnt; jj++) {
+          const int32_t rj = __shfl_sync(FULL, row, jj);
+          if (CODED) {
+            const uint32_t b8 = act0 ? (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(col) + rj) : 0u;
+            s_x[(j0 + jj) * 32 + lane] = (VT)b8;
+            const uint32_t c8 = b8 + coff;  // wide code: 0 NaN, r + 1 for dict[r]
+            mnraw = min(mnraw, c8);
+            mxc = max(mxc, c8);
+            mnc = min(mnc, c8 - 1u);  // NaN (code 0) wraps to the top and never wins
+          } else {
+            const double x = act0 ? __ldg(reinterpret_cast<const double *>(col) + rj) : 0.0;
+            s_x[(j0 + jj) * 32 + lane] = (VT)x;
+            if (x < mn) mn = x;
+            if (x > mx) mx = x;
+            has_nan |= (x != x);
+          }
+        }
+      }
+      uint32_t thr = 0u;
+      if (CODED) {
+        has_nan = (mnraw == 0u);
+        if (act0 && mxc != 0u) {
+          const double *dc8 = p.dict + (int64_t)f * 256;
+          mn = __ldg(dc8 + mnc);
+          mx = __ldg(dc8 + (mxc - 1u));
+        }
       }
       const bool const0 = act0 && (mx <= mn) && !has_nan;  // pkg:236
       const double cut = ET_ADD(mn, ET_MUL(ET_SUB(mx, mn), u));  // pkg:240
-      uint32_t lt = 0, nn = 0;
-      for (int j = 0; j < n; j++) {
-        const double x = s_x[j * 32 + lane];
-        lt |= (uint32_t)(x < cut) << j;
-        nn |= (uint32_t)(x != x) << j;
+      if (CODED) {
+        if (act0 && !const0 && mxc != 0u) {
+          // thr = number of dictionary entries below the cutpoint; all of dict[0, mnc) are, none past mxc - 1
+          const double *dc8 = p.dict + (int64_t)f * 256;
+          uint32_t lo = mnc, hi = mxc;
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(dc8 + mid) < cut)
+              lo = mid + 1u;
+            else
+              hi = mid;
+          }
+          thr = lo;
+        }
+      }
+      // ---- pass 2: side bitmasks over the samples from the parked values
+      uint32_t lt[NW], nn[NW];
+#pragma unroll
+      for (int w = 0; w < NW; w++) {
+        lt[w] = 0u;
+        nn[w] = 0u;
+        if (w < nw) {
+          const int j0 = w << 5, cnt = min(32, n - j0);
+#pragma unroll 8
+          for (int jj = 0; jj < cnt; jj++) {
+            if (CODED) {
+              const uint32_t c8 = (uint32_t)s_x[(j0 + jj) * 32 + lane] + coff;
+              lt[w] |= (uint32_t)((c8 - 1u) < thr) << jj;
+              nn[w] |= (uint32_t)(c8 == 0u) << jj;
+            } else {
+              const double x = (double)s_x[(j0 + jj) * 32 + lane];
+              lt[w] |= (uint32_t)(x < cut) << jj;
+              nn[w] |= (uint32_t)(x != x) << jj;
+            }
+          }
+        }
       }
       // ---- exact score of this lane's candidate (pkg:250-275)
       double s = NAN;
       bool mil = false;
       if (act0 && !const0) {
         double sn, sl = NAN;
-        if (TASK == TASK_CLS) {
-          sn = gini_score_bits(lt, s_cm, C, n, total);
-          if (has_nan) sl = gini_score_bits(lt | nn, s_cm, C, n, total);
-        } else if (TASK == TASK_REG) {
-          sn = var_reduction_bits(lt, s_y, n, total);
-          if (has_nan) sl = var_reduction_bits(lt | nn, s_y, n, total);
-        } else {
-          sn = gini_score_w_bits(lt, s_cm, s_y, C, n, total, nsum);
-          if (has_nan) sl = gini_score_w_bits(lt | nn, s_cm, s_y, C, n, total, nsum);
+        if (TASK == TASK_CLS)
+          sn = gini_score_bits<NW>(lt, s_cm, s_hnode, C, n, nw, total);
+        else if (TASK == TASK_REG)
+          sn = var_reduction_bits<NW>(lt, s_y, n, nw, total);
+        else
+          sn = gini_score_w_bits<NW>(lt, s_cm, s_y, C, n, nw, total, nsum);
+        if (has_nan) {
+          uint32_t ln[NW];
+#pragma unroll
+          for (int w = 0; w < NW; w++) ln[w] = lt[w] | nn[w];
+          if (TASK == TASK_CLS)
+            sl = gini_score_bits<NW>(ln, s_cm, s_hnode, C, n, nw, total);
+          else if (TASK == TASK_REG)
+            sl = var_reduction_bits<NW>(ln, s_y, n, nw, total);
+          else
+            sl = gini_score_w_bits<NW>(ln, s_cm, s_y, C, n, nw, total, nsum);
         }
-        mil = !(sl != sl) && (sl > sn || (sn != sn));
+        mil = !(sl != sl) && (sl > sn || (sn != sn));  // pkg:272-275
         s = mil ? sl : sn;
       }
       // ---- consume the batch in draw (lane) order; the reference stops drawing once k candidates
       //      have been scored, so lanes past that point were never examined
       const bool counted0 = act0 && !const0 && !(s != s);
-      const uint32_t m_cnt0 = __ballot_sync(0xffffffffu, counted0);
+      const uint32_t m_cnt0 = __ballot_sync(FULL, counted0);
       const bool act = act0 && (p.replay || __popc(m_cnt0 & ((1u << lane) - 1u)) < p.k - visited);
       const bool is_const = act && const0;
       const bool is_nan = act && !const0 && (s != s);
       const bool counted = act && counted0;
-      const uint32_t m_act = __ballot_sync(0xffffffffu, act);
-      const uint32_t m_const = __ballot_sync(0xffffffffu, is_const);
-      const uint32_t m_nan = __ballot_sync(0xffffffffu, is_nan);
-      const uint32_t m_cnt = __ballot_sync(0xffffffffu, counted);
+      const uint32_t m_act = __ballot_sync(FULL, act);
+      const uint32_t m_const = __ballot_sync(FULL, is_const);
+      const uint32_t m_nan = __ballot_sync(FULL, is_nan);
+      const uint32_t m_cnt = __ballot_sync(FULL, counted);
       if (p.replay) {
         const bool bad = act && ((is_const && expect != 1) || (is_nan && expect != 3) || (counted && expect != 2));
-        st_mismatch += __popc(__ballot_sync(0xffffffffu, bad));
+        st_mismatch += __popc(__ballot_sync(FULL, bad));
       }
       double bs = counted ? s : -INFINITY;
       int bl = counted ? lane : 64;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        const double os = __shfl_xor_sync(0xffffffffu, bs, o);
-        const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+        const double os = __shfl_xor_sync(FULL, bs, o);
+        const int ol = __shfl_xor_sync(FULL, bl, o);
         if (os > bs || (os == bs && ol < bl)) {
           bs = os;
           bl = ol;
@@ -1403,10 +1547,11 @@ __global__ void __launch_bounds__(32 * TINY_WARPS) k_node_tiny(P p, int32_t qcou
       }
       if (bl < 32 && bs > best_score) {  // strict >: the first best wins (pkg:277)
         best_score = bs;
-        best_feature = __shfl_sync(0xffffffffu, f, bl);
-        best_cut = __shfl_sync(0xffffffffu, cut, bl);
-        best_mil = __shfl_sync(0xffffffffu, (int)mil, bl);
-        best_mask = __shfl_sync(0xffffffffu, mil ? (lt | nn) : lt, bl) & nmask;
+        best_feature = __shfl_sync(FULL, f, bl);
+        best_cut = __shfl_sync(FULL, cut, bl);
+        best_mil = __shfl_sync(FULL, (int)mil, bl);
+#pragma unroll
+        for (int w = 0; w < NW; w++) best_mask[w] = __shfl_sync(FULL, mil ? (lt[w] | nn[w]) : lt[w], bl);
       }
       if (!p.replay && (is_const || is_nan)) atomicOr(&s_const[f >> 5], 1u << (f & 31));
       visited += __popc(m_cnt);
@@ -1444,11 +1589,11 @@ __global__ void __launch_bounds__(32 * TINY_WARPS) k_node_tiny(P p, int32_t qcou
       p.o.cut[node] = NAN;
       p.o.tree[node] = tree;
     }
-    ls = __shfl_sync(0xffffffffu, ls, 0);
+    ls = __shfl_sync(FULL, ls, 0);
     double *lv = p.o.leaf_vals + (int64_t)ls * lw;
     if (TASK == TASK_CLS) {
       const double inv = ET_DIV(1.0, (double)n);
-      for (int c = lane; c < C; c += 32) lv[c] = et_repeat_add(inv, s_hnode[c]);
+      for (int c = lane; c < C; c += 32) lv[c] = et_repeat_add(inv, s_hnode[c]);  // pkg:960-964
     } else if (TASK == TASK_CLSW) {
       for (int c = lane; c < C; c += 32) lv[c] = s_dist[c];
     } else {
@@ -1456,7 +1601,9 @@ __global__ void __launch_bounds__(32 * TINY_WARPS) k_node_tiny(P p, int32_t qcou
     }
     return;
   }
-  const int32_t nl = __popc(best_mask);
+  int32_t nl = 0;
+#pragma unroll
+  for (int w = 0; w < NW; w++) nl += __popc(best_mask[w]);
   int32_t slot = 0;
   if (lane == 0) {
     slot = atomicAdd(&p.cnt->next_f, 2);
@@ -1472,24 +1619,18 @@ __global__ void __launch_bounds__(32 * TINY_WARPS) k_node_tiny(P p, int32_t qcou
       p.nxt.begin[s2] = side ? b + nl : b;
       p.nxt.end[s2] = side ? e : b + nl;
       p.nxt.node[s2] = cl + side;
+      // pkg:870 / 884 (sic): the regression right child keeps currentDepth; pkg:1055,1071: +1 both
       p.nxt.depth[s2] = (TASK == TASK_REG && side) ? depth : depth + 1;
       p.nxt.key[s2] = et_child_key(key, side);
       int64_t tc = -1;
       if (p.replay && tn >= 0) tc = side ? p.tr.right[tn] : p.tr.left[tn];
       p.nxt.trace[s2] = tc;
-      p.q_nxt[0][atomicAdd(&p.cnt->q_count[0], 1)] = s2;  // children of a tiny node are tiny
+      const int qc = size_class(p, side ? (n - nl) : nl);  // (these classes compute their own class histogram)
+      p.q_nxt[qc][atomicAdd(&p.cnt->q_count[qc], 1)] = s2;
     }
     atomicAdd(&p.cnt->st[ST_PROWS], (unsigned long long)n);
   }
-  slot = __shfl_sync(0xffffffffu, slot, 0);
-  if (TASK == TASK_CLS) {
-    int32_t *hl = p.nxt.hist + (int64_t)slot * C, *hr = hl + C;
-    for (int c = lane; c < C; c += 32) {
-      const int32_t a = __popc(s_cm[c] & best_mask);
-      hl[c] = a;
-      hr[c] = s_hnode[c] - a;
-    }
-  }
+  slot = __shfl_sync(FULL, slot, 0);
   if (!p.replay) {
     uint32_t *ml = p.nxt.mask + (int64_t)slot * W, *mr = ml + W;
     for (int w = lane; w < W; w += 32) {
@@ -1499,16 +1640,31 @@ __global__ void __launch_bounds__(32 * TINY_WARPS) k_node_tiny(P p, int32_t qcou
     }
   }
   // the winner's side bitmask is the stable partition (pkg:1024-1039)
-  if (has) {
-    const bool left = (best_mask >> lane) & 1u;
+  {
+    int32_t lpos = b, rpos = b + nl;
     const uint32_t below = (1u << lane) - 1u;
-    const int32_t dst = left ? b + __popc(best_mask & below) : b + nl + __popc(~best_mask & nmask & below);
-    p.idx_dst[base + dst] = row;
-    if (TASK == TASK_REG) {
-      p.yr_dst[base + dst] = yv;
-    } else {
-      p.yc_dst[base + dst] = cls;
-      if (TASK == TASK_CLSW) p.w_dst[base + dst] = wv;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+      if (w < nw) {
+        const int j = w * 32 + lane;
+        const bool has = j < n;
+        const int cnt = min(32, n - w * 32);
+        const uint32_t valid = (cnt >= 32) ? FULL : ((1u << cnt) - 1u);
+        const uint32_t lm = best_mask[w] & valid, rm = ~best_mask[w] & valid;
+        if (has) {
+          const bool left = (lm >> lane) & 1u;
+          const int32_t dst = left ? lpos + __popc(lm & below) : rpos + __popc(rm & below);
+          p.idx_dst[base + dst] = idx[j];
+          if (TASK == TASK_REG) {
+            p.yr_dst[base + dst] = s_y[j];
+          } else {
+            p.yc_dst[base + dst] = p.yc_src[base + b + j];
+            if (TASK == TASK_CLSW) p.w_dst[base + dst] = s_y[j];
+          }
+        }
+        lpos += __popc(lm);
+        rpos += __popc(rm);
+      }
     }
   }
 }
@@ -1696,55 +1852,91 @@ struct EventTimer {
   }
 };
 
-template <int TASK>
-void launch_level(et_ctx *ctx, const P &p, const int32_t *qn, size_t smem_warp, size_t smem_mid, size_t smem_cta,
-                  size_t smem_tiny, PhaseTimer &pt, EventTimer &et) {
+struct LevelCfg {
+  bool coded;
+  size_t smem_warp, smem_mid, smem_cta;  // k_node teams (per team)
+  size_t smem_lane[3];                   // k_lane per warp, classes 0..2
+};
+
+template <int TASK, typename VT, int NW>
+void launch_lane(et_ctx *ctx, const P &p, int32_t count, int qi, size_t smem_per_warp, EventTimer &et) {
   cudaStream_t st = ctx->stream;
-  const int32_t q0 = qn[1], q1 = qn[3];
-  if (qn[2] > 0) {
+  int e0 = et.rec(st);
+  k_lane<TASK, VT, NW><<<(unsigned)ceil_div(count, LANE_WARPS), 32 * LANE_WARPS, smem_per_warp * LANE_WARPS, st>>>(
+      p, count, qi);
+  int e1 = et.rec(st);
+  et.spans[0].push_back({e0, e1});
+  ctx->launches++;
+}
+
+template <int TASK>
+void launch_level(et_ctx *ctx, const P &p, const int32_t *qn, const LevelCfg &lc, PhaseTimer &pt, EventTimer &et) {
+  cudaStream_t st = ctx->stream;
+  // largest teams first: their CTAs run longest, the small-node kernels fill in behind them
+  if (qn[4] > 0) {
     pt.start();
     int e0 = et.rec(st);
-    k_node<TASK, MID_TEAM><<<(unsigned)qn[2], MID_TEAM, smem_mid, st>>>(p, qn[2]);
-    int e1 = et.rec(st);
-    et.spans[1].push_back({e0, e1});
-    ctx->launches++;
-    pt.stop(6);
-  }
-  if (qn[0] > 0) {
-    pt.start();
-    int e0 = et.rec(st);
-    k_node_tiny<TASK><<<(unsigned)ceil_div(qn[0], TINY_WARPS), 32 * TINY_WARPS, smem_tiny * TINY_WARPS, st>>>(p, qn[0]);
-    int e1 = et.rec(st);
-    et.spans[0].push_back({e0, e1});
-    ctx->launches++;
-    pt.stop(7);
-  }
-  if (q0 > 0) {
-    pt.start();
-    int e0 = et.rec(st);
-    k_node<TASK, 32><<<(unsigned)ceil_div(q0, WARPS_PER_CTA), 32 * WARPS_PER_CTA, smem_warp * WARPS_PER_CTA, st>>>(p, q0);
-    int e1 = et.rec(st);
-    et.spans[0].push_back({e0, e1});
-    ctx->launches++;
-    pt.stop(2);
-  }
-  if (q1 > 0) {
-    pt.start();
-    int e0 = et.rec(st);
-    k_node<TASK, CTA_TEAM><<<(unsigned)q1, CTA_TEAM, smem_cta, st>>>(p, q1);
+    k_node<TASK, CTA_TEAM><<<(unsigned)qn[4], CTA_TEAM, lc.smem_cta, st>>>(p, qn[4]);
     int e1 = et.rec(st);
     et.spans[1].push_back({e0, e1});
     ctx->launches++;
     pt.stop(3);
   }
+  if (qn[3] > 0) {
+    pt.start();
+    int e0 = et.rec(st);
+    k_node<TASK, MID_TEAM><<<(unsigned)qn[3], MID_TEAM, lc.smem_mid, st>>>(p, qn[3]);
+    int e1 = et.rec(st);
+    et.spans[1].push_back({e0, e1});
+    ctx->launches++;
+    pt.stop(6);
+  }
+  if (qn[2] > 0) {
+    pt.start();
+    if (lc.coded) {
+      launch_lane<TASK, uint8_t, 16>(ctx, p, qn[2], 2, lc.smem_lane[2], et);
+    } else {
+      int e0 = et.rec(st);
+      k_node<TASK, 32><<<(unsigned)ceil_div(qn[2], WARPS_PER_CTA), 32 * WARPS_PER_CTA, lc.smem_warp * WARPS_PER_CTA, st>>>(
+          p, qn[2]);
+      int e1 = et.rec(st);
+      et.spans[0].push_back({e0, e1});
+      ctx->launches++;
+    }
+    pt.stop(2);
+  }
+  if (qn[1] > 0) {  // byte-coded tables only
+    pt.start();
+    launch_lane<TASK, uint8_t, 4>(ctx, p, qn[1], 1, lc.smem_lane[1], et);
+    pt.stop(2);
+  }
+  if (qn[0] > 0) {
+    pt.start();
+    if (lc.coded)
+      launch_lane<TASK, uint8_t, 1>(ctx, p, qn[0], 0, lc.smem_lane[0], et);
+    else
+      launch_lane<TASK, double, 1>(ctx, p, qn[0], 0, lc.smem_lane[0], et);
+    pt.stop(7);
+  }
 }
 
 template <int TASK>
-void set_smem_attr(size_t smem_warp_total, size_t smem_mid, size_t smem_cta, size_t smem_tiny_total) {
-  CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, MID_TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mid));
-  CUDA_CHECK(cudaFuncSetAttribute(k_node_tiny<TASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tiny_total));
-  CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_warp_total));
-  CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, CTA_TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+void set_smem_attr(const LevelCfg &lc) {
+  CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, MID_TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem_mid));
+  CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, CTA_TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem_cta));
+  if (lc.coded) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, uint8_t, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(lc.smem_lane[0] * LANE_WARPS)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, uint8_t, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(lc.smem_lane[1] * LANE_WARPS)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, uint8_t, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(lc.smem_lane[2] * LANE_WARPS)));
+  } else {
+    CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(lc.smem_lane[0] * LANE_WARPS)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(lc.smem_warp * WARPS_PER_CTA)));
+  }
 }
 
 }  // namespace
@@ -1780,18 +1972,26 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
   const Lay lay_m = make_lay(task, MID_TEAM, C, NB, W, replay);
   if ((size_t)lay_w.bytes * WARPS_PER_CTA > 200 * 1024 || (size_t)lay_c.bytes > 200 * 1024)
     ET_FAIL(ET_EUNSUPPORTED, "numClasses=%d / %d features need more shared memory per node than one SM has", C, d);
-  const size_t tiny_smem = (size_t)tiny_smem_bytes(task, C, W, replay);
-  if (tiny_smem * TINY_WARPS > 200 * 1024)
+  // byte-coded copy of the table (encode.cu): nodes of up to 512 samples are then searched by k_lane
+  if (D->coded == 0) et_data_encode(ctx, D);
+  LevelCfg lc;
+  lc.coded = (D->coded == 1);
+  lc.smem_warp = (size_t)lay_w.bytes;
+  lc.smem_mid = (size_t)lay_m.bytes;
+  lc.smem_cta = (size_t)lay_c.bytes;
+  lc.smem_lane[0] = (size_t)lane_smem_bytes(task, C, W, replay, 1, lc.coded ? 1 : 8);
+  lc.smem_lane[1] = (size_t)lane_smem_bytes(task, C, W, replay, 4, 1);
+  lc.smem_lane[2] = (size_t)lane_smem_bytes(task, C, W, replay, 16, 1);
+  if (lc.coded && lc.smem_lane[2] * LANE_WARPS > 200 * 1024) lc.coded = false;  // (hundreds of classes)
+  if (!lc.coded) lc.smem_lane[0] = (size_t)lane_smem_bytes(task, C, W, replay, 1, 8);
+  if (lc.smem_lane[0] * LANE_WARPS > 200 * 1024)
     ET_FAIL(ET_EUNSUPPORTED, "numClasses=%d / %d features need more shared memory per node than one SM has", C, d);
   if (task == TASK_CLS)
-    set_smem_attr<TASK_CLS>((size_t)lay_w.bytes * WARPS_PER_CTA, (size_t)lay_m.bytes, (size_t)lay_c.bytes,
-                            tiny_smem * TINY_WARPS);
+    set_smem_attr<TASK_CLS>(lc);
   else if (task == TASK_CLSW)
-    set_smem_attr<TASK_CLSW>((size_t)lay_w.bytes * WARPS_PER_CTA, (size_t)lay_m.bytes, (size_t)lay_c.bytes,
-                             tiny_smem * TINY_WARPS);
+    set_smem_attr<TASK_CLSW>(lc);
   else
-    set_smem_attr<TASK_REG>((size_t)lay_w.bytes * WARPS_PER_CTA, (size_t)lay_m.bytes, (size_t)lay_c.bytes,
-                            tiny_smem * TINY_WARPS);
+    set_smem_attr<TASK_REG>(lc);
 
   cudaEvent_t ev0, ev1;
   CUDA_CHECK(cudaEventCreate(&ev0));
@@ -1902,6 +2102,14 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       p.replay = replay ? 1 : 0;
       p.NB = NB;
       p.cnt = ws.cnt.p;
+      p.C8 = lc.coded ? D->c8 : nullptr;
+      p.ldc = D->ldc;
+      p.dict = D->dict;
+      p.coff = D->coff;
+      p.cls_max[0] = NT_MAX;
+      p.cls_max[1] = lc.coded ? 128 : NT_MAX;
+      p.cls_max[2] = NW_MAX;
+      p.cls_max[3] = NM_MAX;
       p.tr = Trace{d_tr_cand_begin, d_tr_cand_count, d_tr_left, d_tr_right, d_tr_cand_feature, d_tr_cand_u,
                    d_tr_cand_flag};
       int srcb = 0, cl = 0;
@@ -1932,8 +2140,8 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
 
       int64_t n_nodes = Bt, n_leaves = 0;
       std::vector<int32_t> level_start{0};
-      int32_t qn[NQ] = {0, 0, 0, 0};
-      qn[size_class(n)] = Bt;
+      int32_t qn[NQ] = {0, 0, 0, 0, 0};
+      qn[size_class(p, n)] = Bt;
       Counters hc;
       memset(&hc, 0, sizeof(hc));
       while (F > 0) {
@@ -1942,8 +2150,8 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
         ws.fr[cl ^ 1].ensure((size_t)F * 2, C, W, task == TASK_CLS, !replay);
         for (int q = 0; q < NQ; q++) ws.q[cl ^ 1][q].ensure((size_t)F * 2, 1.5);
         ws.pool.grow((size_t)(n_nodes + 2 * (int64_t)F), (size_t)n_nodes, (size_t)(n_leaves + F), (size_t)n_leaves, lw, st);
-        if (task != TASK_CLS && qn[2] + qn[3] > 0)
-          ws.scratch.ensure((size_t)NB * 2 * ((size_t)Bt * (size_t)n / 32 + (size_t)(qn[2] + qn[3]) + 1) + 64, 1.0);
+        if (task != TASK_CLS && qn[3] + qn[4] > 0)
+          ws.scratch.ensure((size_t)NB * 2 * ((size_t)Bt * (size_t)n / 32 + (size_t)(qn[3] + qn[4]) + 1) + 64, 1.0);
         pt.stop(0);
         p.idx_src = ws.idx[srcb].p;
         p.idx_dst = ws.idx[srcb ^ 1].p;
@@ -1963,14 +2171,11 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
         p.scratch = ws.scratch.p;
         p.node_base_next = (int32_t)n_nodes;
         if (task == TASK_CLS)
-          launch_level<TASK_CLS>(ctx, p, qn, (size_t)lay_w.bytes, (size_t)lay_m.bytes, (size_t)lay_c.bytes, tiny_smem, pt,
-                                  evt);
+          launch_level<TASK_CLS>(ctx, p, qn, lc, pt, evt);
         else if (task == TASK_CLSW)
-          launch_level<TASK_CLSW>(ctx, p, qn, (size_t)lay_w.bytes, (size_t)lay_m.bytes, (size_t)lay_c.bytes, tiny_smem, pt,
-                                  evt);
+          launch_level<TASK_CLSW>(ctx, p, qn, lc, pt, evt);
         else
-          launch_level<TASK_REG>(ctx, p, qn, (size_t)lay_w.bytes, (size_t)lay_m.bytes, (size_t)lay_c.bytes, tiny_smem, pt,
-                                  evt);
+          launch_level<TASK_REG>(ctx, p, qn, lc, pt, evt);
         pt.start();
         CUDA_CHECK(cudaMemcpyAsync(&hc, ws.cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         // the next level starts from clean per-level counters (leaf count and stats keep accumulating)

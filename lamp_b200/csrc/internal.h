@@ -21,6 +21,12 @@ struct et_data {
   int32_t d = 0;
   int64_t ld = 0;       // column stride in elements (n rounded up to 16)
   double *x = nullptr;  // column-major [d][ld], resident in HBM
+  // order-preserving byte codes of the same table (encode.cu): byte + coff[col] = 0 for NaN, r + 1 for dict[col][r]
+  int coded = 0;           // 0 not prepared yet, 1 codes valid, -1 not codable (> 256 distinct values in a column)
+  uint8_t *c8 = nullptr;   // column-major [d][ldc]
+  uint8_t *coff = nullptr; // [d] 0 if the column holds a NaN, else 1
+  int64_t ldc = 0;         // code column stride in bytes (n rounded up to 128)
+  double *dict = nullptr;  // [d][256] ascending distinct values, padded with +inf
   // attached targets / weights (resident)
   int32_t *y_cls = nullptr;
   int32_t num_classes = 0;
@@ -68,6 +74,8 @@ struct BuildArgs {
   const et_replay *replay;
 };
 
+// encode.cu
+void et_data_encode(et_ctx *ctx, et_data *data);
 // build.cu
 void et_build_forest(et_ctx *ctx, et_data *data, const BuildArgs &a, et_forest *out, et_stats *stats);
 // predict.cu

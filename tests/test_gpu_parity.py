@@ -14,6 +14,14 @@ pytestmark = pytest.mark.gpu
 NAN = float("nan")
 
 
+@pytest.fixture(autouse=True, params=["codes", "fp64"])
+def table_coding(request, monkeypatch):
+    """Every test runs twice: with the byte-coded copy of the table (encode.cu; used whenever all columns
+    have <= 255 distinct values) and with FP64 gathers only (ETGPU_NO_CODES=1)."""
+    monkeypatch.setenv("ETGPU_NO_CODES", "1" if request.param == "fp64" else "0")
+    return request.param
+
+
 # ---- predict ----------------------------------------------------------------------------------------
 def test_predict_classification_matches_oracle(mnist):
     x, y = mnist
