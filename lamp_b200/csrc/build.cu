@@ -48,6 +48,7 @@ constexpr int CTA_TEAM = 512;     // threads of the CTA that owns a larger node
 // (8 B value + 4 B row + 1 B label per sample: 2048 -> 26 KB for the 128-thread team, 8192 -> 104 KB for the
 // 512-thread team, two of which fit one SM)
 __host__ __device__ constexpr int stage_cap(int team) { return team == 32 ? 0 : (team == MID_TEAM ? NM_MAX : 8192); }
+constexpr int CBIG_TEAM = 256;    // threads of the CTA that owns a larger node of a byte-coded table
 constexpr int WARPS_PER_CTA = 4;  // warp teams per CTA in the small-node kernel
 
 // Size classes of the open nodes (upper bounds in P::cls_max; an empty class repeats its predecessor's bound):
@@ -90,15 +91,18 @@ struct Lay {
   int o_u, o_cut, o_score, o_dist, o_redd, o_wh, o_xs, o_ys;                                // doubles
   int o_feat, o_flags, o_nleft, o_hnode, o_besthl, o_hist, o_redi, o_mask, o_bits, o_misc;  // int32
   int o_rows, o_lab, o_cm, o_ord;
+  int o_coloff, o_cred, o_cb, o_thr;  // byte-coded CTA teams: column offsets, reduction scratch, per-candidate bytes
   int hs;      // stride of one candidate's histogram row (odd: conflict-free per-candidate reads)
   int use_cm;  // warp teams: per-chunk class bitmasks fit in shared memory
   int bytes;
 };
 
-__host__ __device__ inline Lay make_lay(int task, int team, int C, int NB, int W, bool replay) {
+__host__ __device__ inline Lay make_lay(int task, int team, int C, int NB, int W, bool replay, bool coded = false) {
   const bool warp_team = (team == 32);
   Lay L;
   int o = 0;  // in 8-byte units first
+  L.o_coloff = o;
+  o += coded ? 32 : 0;
   L.o_u = o;
   o += NB;
   L.o_cut = o;
@@ -112,7 +116,7 @@ __host__ __device__ inline Lay make_lay(int task, int team, int C, int NB, int W
   L.o_wh = o;
   o += (task == TASK_CLSW) ? NB * 2 * C : 0;
   L.o_xs = o;  // warp teams stage the node once: rows, labels / targets, and one candidate's values
-  o += warp_team ? NW_MAX : stage_cap(team);
+  o += warp_team ? NW_MAX : (coded ? 0 : stage_cap(team));
   L.o_ys = o;
   o += (warp_team && task != TASK_CLS) ? NW_MAX : 0;
   int oi = o * 2;  // switch to 4-byte units
@@ -139,6 +143,12 @@ __host__ __device__ inline Lay make_lay(int task, int team, int C, int NB, int W
   oi += 8;
   L.o_ord = oi;
   oi += 32;
+  L.o_cred = oi;
+  oi += coded ? 16 * 24 : 0;
+  L.o_cb = oi;  // 4 byte arrays of 32 candidates: thr - 1, enable, K, nan-enable
+  oi += coded ? 32 : 0;
+  L.o_thr = oi;
+  oi += coded ? 32 : 0;
   L.o_rows = oi;
   oi += warp_team ? NW_MAX : stage_cap(team);
   L.o_lab = oi;  // warp teams: int32 labels; CTA teams: uint8 labels (used when C <= 256)
@@ -412,11 +422,13 @@ __device__ __forceinline__ int32_t rank_select_clear_fast(const uint32_t *taken,
 }
 
 
-template <int TASK, int TEAM>
-__global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM, TEAM == 32 ? 5 : (TEAM == MID_TEAM ? 6 : 2))
-    k_node(P p, int32_t qcount) {
+template <int TASK, int TEAM, bool CODED>
+__global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
+                                  TEAM == 32 ? 5 : (TEAM == MID_TEAM ? (CODED ? 4 : 6) : 2))
+    k_node(P p, int32_t qcount, int qi) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool WARP = (TEAM == 32);
+  static_assert(!CODED || (TASK == TASK_CLS && TEAM > 32), "byte-coded teams: unweighted classification, CTA teams");
   const int tic = WARP ? (threadIdx.x >> 5) : 0;
   const int q = WARP ? blockIdx.x * WARPS_PER_CTA + tic : blockIdx.x;
   if (q >= qcount) return;
@@ -424,7 +436,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM, TEAM =
   const int lane = threadIdx.x & 31;
   const int wit = WARP ? 0 : (threadIdx.x >> 5);  // warp index inside the team
   const int C = p.C, NB = p.NB, W = p.W;
-  const Lay L = make_lay(TASK, TEAM, C, NB, W, p.replay != 0);
+  const Lay L = make_lay(TASK, TEAM, C, NB, W, p.replay != 0, CODED);
   unsigned char *sm = smem_raw + (size_t)tic * L.bytes;
   double *smd = reinterpret_cast<double *>(sm);
   int32_t *smi = reinterpret_cast<int32_t *>(sm);
@@ -436,8 +448,12 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM, TEAM =
   uint32_t *s_bits = reinterpret_cast<uint32_t *>(smi + L.o_bits);
   int32_t *s_misc = smi + L.o_misc, *s_rows = smi + L.o_rows, *s_lab = smi + L.o_lab, *s_ord = smi + L.o_ord;
   uint32_t *s_cm = reinterpret_cast<uint32_t *>(smi + L.o_cm);
+  int64_t *s_coloff = reinterpret_cast<int64_t *>(smd + L.o_coloff);
+  uint32_t *s_cred = reinterpret_cast<uint32_t *>(smi + L.o_cred);
+  uint8_t *s_thrb = reinterpret_cast<uint8_t *>(smi + L.o_cb), *s_enb = s_thrb + 32, *s_Kb = s_thrb + 64, *s_nanb = s_thrb + 96;
+  int32_t *s_thr = smi + L.o_thr;
 
-  const int i = p.q_cur[WARP ? 2 : (TEAM == MID_TEAM ? 3 : 4)][q];
+  const int i = p.q_cur[qi][q];
   const int32_t tree = p.cur.tree[i], b = p.cur.begin[i], e = p.cur.end[i], n = e - b;
   const int32_t node = p.cur.node[i], depth = p.cur.depth[i];
   const int64_t tn = p.cur.trace[i];
@@ -556,6 +572,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM, TEAM =
 
   // ---------------- split search ----------------
   int32_t visited = 0, nconst = 0, best_feature = -1, best_nleft = 0, best_mil = 0;
+  int32_t best_thr = 0, best_K = 0;  // byte-coded tables: the winning split in code space
   double best_score = -INFINITY, best_cut = NAN;
   unsigned long long st_draws = 0, st_const = 0, st_scored = 0, st_mismatch = 0;
   if (!leaf) {
@@ -672,6 +689,157 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM, TEAM =
       if (TASK == TASK_CLS)
         for (int t = tid; t < nb * L.hs; t += TEAM) s_hist[t] = 0;
       team_sync<TEAM>();
+      if (CODED) {
+        // ---- phase 1 (byte-coded table): the team streams the node's samples ONCE per pass for the whole
+        //      batch.  A thread owns a sample and reads its byte in every candidate's column (a warp reads
+        //      32 nearby bytes per column); per-candidate min / max live in packed bytes (4 candidates per
+        //      register), so one pass and one reduction serve the whole batch.
+        if (tid < 32) {
+          const int32_t f = (tid < nb) ? s_feat[tid] : -1;
+          s_coloff[tid] = (int64_t)(f >= 0 ? f : 0) * p.ldc;
+          s_Kb[tid] = (f >= 0 && p.coff[f] == 0) ? 1 : 0;  // wide code - 1 = byte - K (mod 256)
+        }
+        __syncthreads();
+        const int ng = (nb + 3) >> 2;
+        const uint32_t *s_K4 = reinterpret_cast<const uint32_t *>(s_Kb);
+        {
+          uint32_t mnT[8], mxB[8], mnB[8];
+#pragma unroll
+          for (int g = 0; g < 8; g++) {
+            mnT[g] = 0xffffffffu;
+            mxB[g] = 0u;
+            mnB[g] = 0xffffffffu;
+          }
+          for (int32_t j = tid; j < n; j += TEAM) {
+            const int64_t r = rr[j];
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+              if (g < ng) {
+                const uint32_t b0 = __ldg(p.C8 + s_coloff[4 * g + 0] + r), b1 = __ldg(p.C8 + s_coloff[4 * g + 1] + r);
+                const uint32_t b2 = __ldg(p.C8 + s_coloff[4 * g + 2] + r), b3 = __ldg(p.C8 + s_coloff[4 * g + 3] + r);
+                const uint32_t b4 = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+                mxB[g] = __vmaxu4(mxB[g], b4);
+                mnB[g] = __vminu4(mnB[g], b4);
+                mnT[g] = __vminu4(mnT[g], __vsub4(b4, s_K4[g]));  // NaN (byte 0 of a column with NaNs) -> 255
+              }
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < 8; g++) {
+            if (g < ng) {
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                mxB[g] = __vmaxu4(mxB[g], __shfl_xor_sync(0xffffffffu, mxB[g], o));
+                mnB[g] = __vminu4(mnB[g], __shfl_xor_sync(0xffffffffu, mnB[g], o));
+                mnT[g] = __vminu4(mnT[g], __shfl_xor_sync(0xffffffffu, mnT[g], o));
+              }
+              if (lane == 0) {
+                s_cred[wit * 24 + g] = mnT[g];
+                s_cred[wit * 24 + 8 + g] = mxB[g];
+                s_cred[wit * 24 + 16 + g] = mnB[g];
+              }
+            }
+          }
+        }
+        __syncthreads();
+        // ---- per candidate: decode min / max, constant test, cutpoint, code threshold
+        if (wit == 0) {
+          bool nan_c = false;
+          const int c = lane;
+          const int32_t f = (c < nb) ? s_feat[c] : -1;
+          s_enb[c] = 0;
+          s_nanb[c] = 0;
+          s_thrb[c] = 0;
+          if (f >= 0) {
+            const int g = c >> 2, sh = 8 * (c & 3);
+            uint32_t mnt = 255u, mxb = 0u, mnb = 255u;
+            for (int w2 = 0; w2 < TEAM / 32; w2++) {
+              mnt = min(mnt, (s_cred[w2 * 24 + g] >> sh) & 255u);
+              mxb = max(mxb, (s_cred[w2 * 24 + 8 + g] >> sh) & 255u);
+              mnb = min(mnb, (s_cred[w2 * 24 + 16 + g] >> sh) & 255u);
+            }
+            const uint32_t K = s_Kb[c], wmax = mxb + (1u - K);  // largest wide code (0 = only NaNs)
+            const bool has_nan = (K == 1u) && (mnb == 0u);
+            double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;  // pkg:35-36
+            const double *dc8 = p.dict + (int64_t)f * 256;
+            if (wmax != 0u) {
+              mn = __ldg(dc8 + mnt);
+              mx = __ldg(dc8 + (wmax - 1u));
+            }
+            if (mx <= mn && !has_nan) {  // pkg:236
+              s_flags[c] |= CF_CONST;
+            } else {
+              const double cut = ET_ADD(mn, ET_MUL(ET_SUB(mx, mn), s_u[c]));  // nextDouble(min, max), pkg:240
+              uint32_t thr = 0u;  // number of dictionary entries below the cutpoint
+              if (wmax != 0u) {
+                uint32_t lo = mnt, hi = wmax;
+                while (lo < hi) {
+                  const uint32_t mid = (lo + hi) >> 1;
+                  if (__ldg(dc8 + mid) < cut)
+                    lo = mid + 1u;
+                  else
+                    hi = mid;
+                }
+                thr = lo;
+              }
+              s_cut[c] = cut;
+              s_thr[c] = (int32_t)thr;
+              s_thrb[c] = (uint8_t)(thr > 0u ? thr - 1u : 0u);
+              s_enb[c] = thr > 0u ? 0xff : 0;
+              if (has_nan) {
+                s_flags[c] |= CF_NAN;
+                s_nanb[c] = 0xff;
+                nan_c = true;
+              }
+            }
+          }
+          const bool any_nan = __any_sync(0xffffffffu, nan_c);
+          if (lane == 0) s_misc[3] = any_nan ? 1 : 0;
+        }
+        __syncthreads();
+        // ---- pass 2: side histograms.  Per 32 consecutive samples: one ballot per candidate, counted
+        //      against the class masks with lane == class.
+        const int nsweep = s_misc[3] ? 2 : 1;  // second sweep: NaN rows per class (pkg:244-248)
+        for (int sweep = 0; sweep < nsweep; sweep++) {
+          int32_t acc[32];
+#pragma unroll
+          for (int c = 0; c < 32; c++) acc[c] = 0;
+          const uint32_t *s_t4 = reinterpret_cast<const uint32_t *>(s_thrb);
+          const uint32_t *s_e4 = reinterpret_cast<const uint32_t *>(sweep ? s_nanb : s_enb);
+          for (int32_t j0 = wit * 32; j0 < n; j0 += TEAM) {
+            const int32_t j = j0 + lane;
+            const bool valid = j < n;
+            const int64_t r = valid ? rr[j] : 0;
+            const int32_t cls = valid ? LAB(j) : -1;
+            uint32_t cmk = 0u;  // samples of this chunk whose class is this lane's index
+            for (int q2 = 0; q2 < C; q2++) {
+              const uint32_t m = __ballot_sync(0xffffffffu, cls == q2);
+              if (lane == q2) cmk = m;
+            }
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+              if (g < ng) {
+                const uint32_t b0 = __ldg(p.C8 + s_coloff[4 * g + 0] + r), b1 = __ldg(p.C8 + s_coloff[4 * g + 1] + r);
+                const uint32_t b2 = __ldg(p.C8 + s_coloff[4 * g + 2] + r), b3 = __ldg(p.C8 + s_coloff[4 * g + 3] + r);
+                const uint32_t b4 = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+                uint32_t l4 = sweep ? __vcmpeq4(b4, 0u) : __vcmpleu4(__vsub4(b4, s_K4[g]), s_t4[g]);
+                l4 &= s_e4[g];
+                if (!valid) l4 = 0u;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; q4++) {
+                  const uint32_t bal = __ballot_sync(0xffffffffu, (l4 >> (8 * q4)) & 1u);
+                  acc[4 * g + q4] += __popc(bal & cmk);
+                }
+              }
+            }
+          }
+          if (lane < C) {
+#pragma unroll
+            for (int c = 0; c < 32; c++)
+              if (c < nb && acc[c]) atomicAdd(&s_hist[c * L.hs + (sweep ? C : 0) + lane], acc[c]);
+          }
+        }
+      } else {
       // ---- phase 1: the whole team on the samples of one candidate at a time
       for (int oi = 0; oi < 32; oi++) {
         const int c = s_ord[oi];
@@ -852,6 +1020,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM, TEAM =
           }
         }
       }
+      }
       team_sync<TEAM>();
       // ---- phase 2: one thread per candidate evaluates the reference's score expression exactly
       if (tid < nb && s_feat[tid] >= 0 && !(s_flags[tid] & CF_CONST)) {
@@ -924,6 +1093,10 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM, TEAM =
           best_cut = s_cut[bl];
           best_mil = (s_flags[bl] & CF_MIL) ? 1 : 0;
           best_nleft = s_nleft[bl];
+          if (CODED) {
+            best_thr = s_thr[bl];
+            best_K = s_Kb[bl];
+          }
           if (TASK == TASK_CLS && wit == 0) {
             const int32_t *hl = s_hist + bl * L.hs;
             for (int c = lane; c < C; c += 32) s_besthl[c] = hl[c] + (best_mil ? hl[C + c] : 0);
@@ -1038,8 +1211,14 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM, TEAM =
       bool left = false;
       if (valid) {
         r = rr[j];
-        const double x = __ldg(col + r);
-        left = (x < best_cut) || (mil && (x != x));
+        if (CODED) {
+          const int32_t b8 = (int32_t)__ldg(p.C8 + (int64_t)best_feature * p.ldc + r);
+          const bool isn = (best_K == 1) && (b8 == 0);
+          left = isn ? mil : (((b8 - best_K) & 255) < best_thr);
+        } else {
+          const double x = __ldg(col + r);
+          left = (x < best_cut) || (mil && (x != x));
+        }
       }
       const uint32_t bv = __ballot_sync(0xffffffffu, valid);
       const uint32_t bl = __ballot_sync(0xffffffffu, left);
@@ -1853,7 +2032,8 @@ struct EventTimer {
 };
 
 struct LevelCfg {
-  bool coded;
+  bool coded;      // nodes of up to 512 samples: k_lane on byte codes
+  bool coded_big;  // larger nodes: byte-coded CTA teams (unweighted classification, <= 32 classes)
   size_t smem_warp, smem_mid, smem_cta;  // k_node teams (per team)
   size_t smem_lane[3];                   // k_lane per warp, classes 0..2
 };
@@ -1869,6 +2049,12 @@ void launch_lane(et_ctx *ctx, const P &p, int32_t count, int qi, size_t smem_per
   ctx->launches++;
 }
 
+// the byte-coded CTA teams exist for unweighted classification only
+template <int TASK, int TEAM>
+void launch_coded_team(const P &p, int32_t count, int qi, size_t smem, cudaStream_t st) {
+  if constexpr (TASK == TASK_CLS) k_node<TASK_CLS, TEAM, true><<<(unsigned)count, TEAM, smem, st>>>(p, count, qi);
+}
+
 template <int TASK>
 void launch_level(et_ctx *ctx, const P &p, const int32_t *qn, const LevelCfg &lc, PhaseTimer &pt, EventTimer &et) {
   cudaStream_t st = ctx->stream;
@@ -1876,7 +2062,10 @@ void launch_level(et_ctx *ctx, const P &p, const int32_t *qn, const LevelCfg &lc
   if (qn[4] > 0) {
     pt.start();
     int e0 = et.rec(st);
-    k_node<TASK, CTA_TEAM><<<(unsigned)qn[4], CTA_TEAM, lc.smem_cta, st>>>(p, qn[4]);
+    if (lc.coded_big)
+      launch_coded_team<TASK, CBIG_TEAM>(p, qn[4], 4, lc.smem_cta, st);
+    else
+      k_node<TASK, CTA_TEAM, false><<<(unsigned)qn[4], CTA_TEAM, lc.smem_cta, st>>>(p, qn[4], 4);
     int e1 = et.rec(st);
     et.spans[1].push_back({e0, e1});
     ctx->launches++;
@@ -1885,7 +2074,10 @@ void launch_level(et_ctx *ctx, const P &p, const int32_t *qn, const LevelCfg &lc
   if (qn[3] > 0) {
     pt.start();
     int e0 = et.rec(st);
-    k_node<TASK, MID_TEAM><<<(unsigned)qn[3], MID_TEAM, lc.smem_mid, st>>>(p, qn[3]);
+    if (lc.coded_big)
+      launch_coded_team<TASK, MID_TEAM>(p, qn[3], 3, lc.smem_mid, st);
+    else
+      k_node<TASK, MID_TEAM, false><<<(unsigned)qn[3], MID_TEAM, lc.smem_mid, st>>>(p, qn[3], 3);
     int e1 = et.rec(st);
     et.spans[1].push_back({e0, e1});
     ctx->launches++;
@@ -1897,8 +2089,8 @@ void launch_level(et_ctx *ctx, const P &p, const int32_t *qn, const LevelCfg &lc
       launch_lane<TASK, uint8_t, 16>(ctx, p, qn[2], 2, lc.smem_lane[2], et);
     } else {
       int e0 = et.rec(st);
-      k_node<TASK, 32><<<(unsigned)ceil_div(qn[2], WARPS_PER_CTA), 32 * WARPS_PER_CTA, lc.smem_warp * WARPS_PER_CTA, st>>>(
-          p, qn[2]);
+      k_node<TASK, 32, false>
+          <<<(unsigned)ceil_div(qn[2], WARPS_PER_CTA), 32 * WARPS_PER_CTA, lc.smem_warp * WARPS_PER_CTA, st>>>(p, qn[2], 2);
       int e1 = et.rec(st);
       et.spans[0].push_back({e0, e1});
       ctx->launches++;
@@ -1922,8 +2114,19 @@ void launch_level(et_ctx *ctx, const P &p, const int32_t *qn, const LevelCfg &lc
 
 template <int TASK>
 void set_smem_attr(const LevelCfg &lc) {
-  CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, MID_TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem_mid));
-  CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, CTA_TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem_cta));
+  if (lc.coded_big) {
+    if constexpr (TASK == TASK_CLS) {
+      CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK_CLS, MID_TEAM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)lc.smem_mid));
+      CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK_CLS, CBIG_TEAM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)lc.smem_cta));
+    }
+  } else {
+    CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, MID_TEAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)lc.smem_mid));
+    CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, CTA_TEAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)lc.smem_cta));
+  }
   if (lc.coded) {
     CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, uint8_t, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(lc.smem_lane[0] * LANE_WARPS)));
@@ -1934,7 +2137,7 @@ void set_smem_attr(const LevelCfg &lc) {
   } else {
     CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(lc.smem_lane[0] * LANE_WARPS)));
-    CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(lc.smem_warp * WARPS_PER_CTA)));
   }
 }
@@ -1983,6 +2186,11 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
   lc.smem_lane[1] = (size_t)lane_smem_bytes(task, C, W, replay, 4, 1);
   lc.smem_lane[2] = (size_t)lane_smem_bytes(task, C, W, replay, 16, 1);
   if (lc.coded && lc.smem_lane[2] * LANE_WARPS > 200 * 1024) lc.coded = false;  // (hundreds of classes)
+  lc.coded_big = lc.coded && task == TASK_CLS && C <= 32;
+  if (lc.coded_big) {
+    lc.smem_mid = (size_t)make_lay(task, MID_TEAM, C, NB, W, replay, true).bytes;
+    lc.smem_cta = (size_t)make_lay(task, CBIG_TEAM, C, NB, W, replay, true).bytes;
+  }
   if (!lc.coded) lc.smem_lane[0] = (size_t)lane_smem_bytes(task, C, W, replay, 1, 8);
   if (lc.smem_lane[0] * LANE_WARPS > 200 * 1024)
     ET_FAIL(ET_EUNSUPPORTED, "numClasses=%d / %d features need more shared memory per node than one SM has", C, d);
