@@ -54,6 +54,11 @@ extern "C" int et_init(int32_t device, et_ctx **out) {
   c->sm_count = prop.multiProcessorCount;
   CUDA_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
+  CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < 7; i++) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+  }
   *out = c;
   ET_API_END
 }
@@ -63,6 +68,11 @@ extern "C" void et_shutdown(et_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  for (int i = 0; i < 7; i++) {
+    if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+    if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   et_workspace_free(ctx->ws);
   delete ctx;
 }

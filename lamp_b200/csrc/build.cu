@@ -52,10 +52,12 @@ constexpr int CBIG_TEAM = 256;    // threads of the CTA that owns a larger node 
 constexpr int WARPS_PER_CTA = 4;  // warp teams per CTA in the small-node kernel
 
 // Size classes of the open nodes (upper bounds in P::cls_max; an empty class repeats its predecessor's bound):
-//   0, 1, 2  one warp per node, one lane per candidate (k_lane; classes 1, 2 only on byte-coded tables)
-//   2        (FP64 tables) one warp per node, lanes on samples (k_node<32>)
-//   3, 4     one CTA per node (k_node<128>, k_node<512>)
-constexpr int NQ = 5;
+//   0..4  n <= 32, 64, 128, 256, 512: one warp per node, one lane per candidate (k_lane; classes 1..4 only
+//         on byte-coded tables, each with shared memory sized to its bound)
+//   4     (FP64 tables) n <= 512: one warp per node, lanes on samples (k_node<32>)
+//   5, 6  n <= 2048, larger: one CTA per node (k_node)
+constexpr int NQ = 7;
+constexpr int Q_WARP = 4, Q_MID = 5, Q_CTA = 6;
 
 struct Counters {
   int32_t next_f;
@@ -222,6 +224,9 @@ __global__ void k_init_roots(P p, int32_t B, const uint64_t *tree_keys, const in
   p.q_cur[size_class(p, p.n)][t] = t;
 }
 
+// (kept out of line: the closed form is long and is called from several places of every node kernel)
+__device__ __noinline__ double repeat_add_dev(double c, int64_t h) { return et_repeat_add(c, h); }
+
 // ---- team helpers ---------------------------------------------------------------------------
 template <int TEAM>
 __device__ __forceinline__ void team_sync() {
@@ -284,7 +289,7 @@ __device__ __forceinline__ bool team_all(bool v, int32_t *redi) {
 // ---- exact scores ---------------------------------------------------------------------------
 // giniScore (pkg:1101-1158, unweighted) from integer histograms: hin[c] = hl[c] (+ hn[c] when NaN
 // rows go left); hout = node histogram - hin.
-__device__ double gini_score_int(const int32_t *hnode, const int32_t *hl, const int32_t *hn, bool nan_left, int C,
+__device__ __noinline__ double gini_score_int(const int32_t *hnode, const int32_t *hl, const int32_t *hn, bool nan_left, int C,
                                  int32_t n, double G, int32_t *cin_out) {
   int32_t cin_i = 0;
   for (int c = 0; c < C; c++) cin_i += hl[c] + (nan_left ? hn[c] : 0);
@@ -501,7 +506,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
     if (!leaf) {
       // giniImpurity with the reference's repeated `+= 1/s` distribution (pkg:905-911, 1160-1180)
       const double inv = ET_DIV(1.0, (double)n);
-      for (int c = tid; c < C; c += TEAM) s_dist[c] = et_repeat_add(inv, s_hnode[c]);
+      for (int c = tid; c < C; c += TEAM) s_dist[c] = repeat_add_dev(inv, s_hnode[c]);
       team_sync<TEAM>();
       double s = 0.0;
       for (int c = 0; c < C; c++) s = ET_ADD(s, ET_MUL(s_dist[c], s_dist[c]));
@@ -1145,7 +1150,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
     double *lv = p.o.leaf_vals + (int64_t)s_misc[2] * lw;
     if (TASK == TASK_CLS) {
       const double inv = ET_DIV(1.0, (double)n);
-      for (int c = tid; c < C; c += TEAM) lv[c] = et_repeat_add(inv, s_hnode[c]);  // pkg:960-964
+      for (int c = tid; c < C; c += TEAM) lv[c] = repeat_add_dev(inv, s_hnode[c]);  // pkg:960-964
     } else if (TASK == TASK_CLSW) {
       for (int c = tid; c < C; c += TEAM) lv[c] = s_dist[c];
     } else {
@@ -1268,7 +1273,8 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
 // VT = uint8_t gathers the order-preserving byte codes of encode.cu (wide code 0 = NaN, r + 1 = dict[r]):
 // min / max are integer, decoded through the dictionary, and `x < cut` is `code - 1 < thr` with
 // thr = number of dictionary entries below the cutpoint -- bit-identical decisions on 1/8 of the bytes,
-// and a node of up to 512 samples parks in 16 KB.
+// and a node of up to 512 samples parks in 16 KB.  NW (32-sample words per node) is a launch
+// parameter: one size class per NW in {1, 2, 4, 8, 16}, shared memory sized to the class.
 constexpr int LANE_WARPS = 4;
 
 __host__ __device__ inline int lane_smem_bytes(int task, int C, int W, bool replay, int NW, int vbytes) {
@@ -1276,21 +1282,25 @@ __host__ __device__ inline int lane_smem_bytes(int task, int C, int W, bool repl
   o += (task == TASK_CLS) ? 0 : 32 * NW * 8;      // s_y    regression target / weight, by position
   o += (task == TASK_REG) ? 0 : C * 8;            // s_dist
   o += 32 * NW * 32 * vbytes;                     // s_x    parked values [position][lane]
+  o += 2 * NW * 32 * 4;                           // s_lt, s_nn  side bitmasks [word][lane]
+  o += NW * 4;                                    // s_best winner's bitmask
   o += (task == TASK_REG) ? 0 : C * NW * 4;       // s_cm   per class, bitmask over the positions
   o += (task == TASK_REG) ? 0 : C * 4;            // s_hnode
   o += replay ? 0 : 2 * W * 4;                    // const / taken masks
   return ((o + 15) / 16) * 16;
 }
 
+// this lane's side bitmask word w: samples with x < cut, plus the NaN samples when they go left
+#define LANE_IN(w) (s_lt[(w) * 32 + lane] | (nan_left ? s_nn[(w) * 32 + lane] : 0u))
+
 // giniScore from a side bitmask (bit j = sample j goes left) and per-class sample bitmasks.
 // Classes absent from the node contribute exactly +0.0 to both sums and are skipped; an empty side
 // gives 0/0 = NaN exactly like the reference (pkg:1148-1157).
-template <int NW>
-__device__ __forceinline__ double gini_score_bits(const uint32_t (&in)[NW], const uint32_t *cm, const int32_t *hnode,
-                                                  int C, int32_t n, int nw, double G) {
+__device__ __noinline__ double gini_score_bits(const uint32_t *s_lt, const uint32_t *s_nn, bool nan_left, int lane,
+                                                  const uint32_t *cm, const int32_t *hnode, int C, int32_t n, int nw,
+                                                  int NW, double G) {
   int32_t cin_i = 0;
-#pragma unroll
-  for (int w = 0; w < NW; w++) cin_i += __popc(in[w]);
+  for (int w = 0; w < nw; w++) cin_i += __popc(LANE_IN(w));
   if (cin_i == 0 || cin_i == n) return NAN;
   const double cin = (double)cin_i, cout = (double)(n - cin_i), N = (double)n;
   double sin_ = 0.0, sout = 0.0;
@@ -1298,9 +1308,7 @@ __device__ __forceinline__ double gini_score_bits(const uint32_t (&in)[NW], cons
     const int32_t ht = hnode[c];
     if (ht == 0) continue;
     int32_t hi = 0;
-#pragma unroll
-    for (int w = 0; w < NW; w++)
-      if (w < nw) hi += __popc(cm[c * NW + w] & in[w]);
+    for (int w = 0; w < nw; w++) hi += __popc(cm[c * NW + w] & LANE_IN(w));
     const int32_t ho = ht - hi;
     const double pi = ET_DIV((double)hi, cin), po = ET_DIV((double)ho, cout);
     sin_ = ET_ADD(sin_, ET_MUL(pi, pi));
@@ -1313,37 +1321,33 @@ __device__ __forceinline__ double gini_score_bits(const uint32_t (&in)[NW], cons
 // weighted giniScore (pkg:1132-1157): per-class and per-side sums in subset order.  Each of the
 // reference's accumulators only ever sees its own samples, so walking the samples class by class
 // (in subset order inside a class) performs the same additions in the same order.
-template <int NW>
-__device__ __forceinline__ double gini_score_w_bits(const uint32_t (&in)[NW], const uint32_t *cm, const double *w,
-                                                    int C, int32_t n, int nw, double G, double N) {
+__device__ __noinline__ double gini_score_w_bits(const uint32_t *s_lt, const uint32_t *s_nn, bool nan_left, int lane,
+                                                    const uint32_t *cm, const double *wgt, int C, int32_t n, int nw,
+                                                    int NW, double G, double N) {
   double cin = 0.0, cout = 0.0;
-#pragma unroll
-  for (int v = 0; v < NW; v++) {
-    if (v < nw) {
-      const int cnt = min(32, n - v * 32);
-      for (int j = 0; j < cnt; j++) {
-        if ((in[v] >> j) & 1u)
-          cin = ET_ADD(cin, w[v * 32 + j]);
-        else
-          cout = ET_ADD(cout, w[v * 32 + j]);
-      }
+  for (int v = 0; v < nw; v++) {
+    const uint32_t in = LANE_IN(v);
+    const int cnt = min(32, n - v * 32);
+    for (int j = 0; j < cnt; j++) {
+      if ((in >> j) & 1u)
+        cin = ET_ADD(cin, wgt[v * 32 + j]);
+      else
+        cout = ET_ADD(cout, wgt[v * 32 + j]);
     }
   }
   double sin_ = 0.0, sout = 0.0;
   for (int c = 0; c < C; c++) {
     double hi = 0.0, ho = 0.0;
-#pragma unroll
-    for (int v = 0; v < NW; v++) {
-      if (v < nw) {
-        uint32_t m = cm[c * NW + v];
-        while (m) {
-          const int j = __ffs(m) - 1;
-          m &= m - 1;
-          if ((in[v] >> j) & 1u)
-            hi = ET_ADD(hi, w[v * 32 + j]);
-          else
-            ho = ET_ADD(ho, w[v * 32 + j]);
-        }
+    for (int v = 0; v < nw; v++) {
+      const uint32_t in = LANE_IN(v);
+      uint32_t m = cm[c * NW + v];
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        if ((in >> j) & 1u)
+          hi = ET_ADD(hi, wgt[v * 32 + j]);
+        else
+          ho = ET_ADD(ho, wgt[v * 32 + j]);
       }
     }
     const double pi = ET_DIV(hi, cin), po = ET_DIV(ho, cout);
@@ -1355,40 +1359,35 @@ __device__ __forceinline__ double gini_score_w_bits(const uint32_t (&in)[NW], co
 }
 
 // computeVarianceReduction (pkg:1196-1218) from a side bitmask, sequential in subset order
-template <int NW>
-__device__ __forceinline__ double var_reduction_bits(const uint32_t (&in)[NW], const double *y, int32_t n, int nw,
-                                                     double V) {
+__device__ __noinline__ double var_reduction_bits(const uint32_t *s_lt, const uint32_t *s_nn, bool nan_left, int lane,
+                                                     const double *y, int32_t n, int nw, double V) {
   double sin_ = 0.0, sout = 0.0;
   int32_t nin = 0;
-#pragma unroll
-  for (int v = 0; v < NW; v++) {
-    if (v < nw) {
-      nin += __popc(in[v]);
-      const int cnt = min(32, n - v * 32);
-      for (int j = 0; j < cnt; j++) {
-        if ((in[v] >> j) & 1u)
-          sin_ = ET_ADD(sin_, y[v * 32 + j]);
-        else
-          sout = ET_ADD(sout, y[v * 32 + j]);
-      }
+  for (int v = 0; v < nw; v++) {
+    const uint32_t in = LANE_IN(v);
+    nin += __popc(in);
+    const int cnt = min(32, n - v * 32);
+    for (int j = 0; j < cnt; j++) {
+      if ((in >> j) & 1u)
+        sin_ = ET_ADD(sin_, y[v * 32 + j]);
+      else
+        sout = ET_ADD(sout, y[v * 32 + j]);
     }
   }
   const int32_t nout = n - nin;
   const double dnin = (double)nin, dnout = (double)nout, dn = (double)n;
   const double min_ = ET_DIV(sin_, dnin), mout = ET_DIV(sout, dnout);
   double qin = 0.0, qout = 0.0;
-#pragma unroll
-  for (int v = 0; v < NW; v++) {
-    if (v < nw) {
-      const int cnt = min(32, n - v * 32);
-      for (int j = 0; j < cnt; j++) {
-        if ((in[v] >> j) & 1u) {
-          const double dl = ET_SUB(y[v * 32 + j], min_);
-          qin = ET_ADD(qin, ET_MUL(dl, dl));
-        } else {
-          const double dl = ET_SUB(y[v * 32 + j], mout);
-          qout = ET_ADD(qout, ET_MUL(dl, dl));
-        }
+  for (int v = 0; v < nw; v++) {
+    const uint32_t in = LANE_IN(v);
+    const int cnt = min(32, n - v * 32);
+    for (int j = 0; j < cnt; j++) {
+      if ((in >> j) & 1u) {
+        const double dl = ET_SUB(y[v * 32 + j], min_);
+        qin = ET_ADD(qin, ET_MUL(dl, dl));
+      } else {
+        const double dl = ET_SUB(y[v * 32 + j], mout);
+        qout = ET_ADD(qout, ET_MUL(dl, dl));
       }
     }
   }
@@ -1401,8 +1400,8 @@ __device__ __forceinline__ double var_reduction_bits(const uint32_t (&in)[NW], c
   return ET_DIV(ET_SUB(ET_SUB(V, a), bq), V);
 }
 
-template <int TASK, typename VT, int NW>
-__global__ void __launch_bounds__(32 * LANE_WARPS) k_lane(P p, int32_t qcount, int qi) {
+template <int TASK, typename VT>
+__global__ void __launch_bounds__(32 * LANE_WARPS) k_lane(P p, int32_t qcount, int qi, int NW) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool CODED = (sizeof(VT) != 8);
   constexpr uint32_t FULL = 0xffffffffu;
@@ -1414,7 +1413,10 @@ __global__ void __launch_bounds__(32 * LANE_WARPS) k_lane(P p, int32_t qcount, i
   double *s_y = reinterpret_cast<double *>(sm);
   double *s_dist = s_y + ((TASK == TASK_CLS) ? 0 : 32 * NW);
   VT *s_x = reinterpret_cast<VT *>(s_dist + ((TASK == TASK_REG) ? 0 : C));
-  uint32_t *s_cm = reinterpret_cast<uint32_t *>(s_x + 32 * NW * 32);
+  uint32_t *s_lt = reinterpret_cast<uint32_t *>(s_x + 32 * NW * 32);
+  uint32_t *s_nn = s_lt + NW * 32;
+  uint32_t *s_best = s_nn + NW * 32;
+  uint32_t *s_cm = s_best + NW;
   int32_t *s_hnode = reinterpret_cast<int32_t *>(s_cm + ((TASK == TASK_REG) ? 0 : C * NW));
   uint32_t *s_const = reinterpret_cast<uint32_t *>(s_hnode + ((TASK == TASK_REG) ? 0 : C)), *s_taken = s_const + W;
 
@@ -1433,15 +1435,12 @@ __global__ void __launch_bounds__(32 * LANE_WARPS) k_lane(P p, int32_t qcount, i
     for (int t = lane; t < C * NW; t += 32) s_cm[t] = 0u;
     __syncwarp();
     const int32_t *yc = p.yc_src + base + b;
-#pragma unroll
-    for (int w = 0; w < NW; w++) {
-      if (w < nw) {
-        const int j = w * 32 + lane;
-        const bool has = j < n;
-        const int32_t cls = has ? yc[j] : -1;
-        const uint32_t grp = __match_any_sync(FULL, cls);
-        if (has && lane == __ffs(grp) - 1) s_cm[cls * NW + w] = grp;
-      }
+    for (int w = 0; w < nw; w++) {
+      const int j = w * 32 + lane;
+      const bool has = j < n;
+      const int32_t cls = has ? yc[j] : -1;
+      const uint32_t grp = __match_any_sync(FULL, cls);
+      if (has && lane == __ffs(grp) - 1) s_cm[cls * NW + w] = grp;
     }
   }
   if (TASK == TASK_REG) {
@@ -1461,9 +1460,7 @@ __global__ void __launch_bounds__(32 * LANE_WARPS) k_lane(P p, int32_t qcount, i
     bool pure_l = false;
     for (int c = lane; c < C; c += 32) {
       int32_t h = 0;
-#pragma unroll
-      for (int w = 0; w < NW; w++)
-        if (w < nw) h += __popc(s_cm[c * NW + w]);
+      for (int w = 0; w < nw; w++) h += __popc(s_cm[c * NW + w]);
       s_hnode[c] = h;
       pure_l |= (h == n);
     }
@@ -1475,7 +1472,7 @@ __global__ void __launch_bounds__(32 * LANE_WARPS) k_lane(P p, int32_t qcount, i
     if (!leaf) {
       // giniImpurity with the reference's repeated `+= 1/s` distribution (pkg:905-911, 1160-1180)
       const double inv = ET_DIV(1.0, (double)n);
-      for (int c = lane; c < C; c += 32) s_dist[c] = et_repeat_add(inv, s_hnode[c]);
+      for (int c = lane; c < C; c += 32) s_dist[c] = repeat_add_dev(inv, s_hnode[c]);
       __syncwarp();
       double s = 0.0;
       for (int c = 0; c < C; c++) s = ET_ADD(s, ET_MUL(s_dist[c], s_dist[c]));
@@ -1510,15 +1507,12 @@ __global__ void __launch_bounds__(32 * LANE_WARPS) k_lane(P p, int32_t qcount, i
     for (int j = 0; j < n; j++) s = ET_ADD(s, s_y[j]);
     for (int c = lane; c < C; c += 32) {
       double a = 0.0;
-#pragma unroll
-      for (int w = 0; w < NW; w++) {
-        if (w < nw) {
-          uint32_t m = s_cm[c * NW + w];
-          while (m) {
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            a = ET_ADD(a, s_y[w * 32 + j]);
-          }
+      for (int w = 0; w < nw; w++) {
+        uint32_t m = s_cm[c * NW + w];
+        while (m) {
+          const int j = __ffs(m) - 1;
+          m &= m - 1;
+          a = ET_ADD(a, s_y[w * 32 + j]);
         }
       }
       s_dist[c] = ET_DIV(a, s);
@@ -1532,9 +1526,6 @@ __global__ void __launch_bounds__(32 * LANE_WARPS) k_lane(P p, int32_t qcount, i
 
   // ---------------- split search ----------------
   int32_t visited = 0, nconst = 0, best_feature = -1, best_mil = 0;
-  uint32_t best_mask[NW];
-#pragma unroll
-  for (int w = 0; w < NW; w++) best_mask[w] = 0u;
   double best_score = -INFINITY, best_cut = NAN;
   unsigned long long st_draws = 0, st_const = 0, st_scored = 0, st_mismatch = 0;
   if (!leaf) {
@@ -1600,46 +1591,54 @@ __global__ void __launch_bounds__(32 * LANE_WARPS) k_lane(P p, int32_t qcount, i
                             : reinterpret_cast<const VT *>(p.X) + (int64_t)(act0 ? f : 0) * p.ld;
       double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;  // pkg:35-36
       bool has_nan = false;
-      uint32_t mnc = 0xffffffffu, mxc = 0u, mnraw = 0xffffffffu;
-      const uint32_t coff = (CODED && act0) ? (uint32_t)__ldg(p.coff + f) : 0u;
+      // byte codes: K = 1 in a column that holds NaNs (stored byte 0 = NaN), else 0; t = byte - K is the
+      // dictionary rank (NaN wraps to the top and never wins the min); the largest byte gives the max
+      const uint32_t K = (CODED && act0 && __ldg(p.coff + f) == 0) ? 1u : 0u;
+      const bool nan_cols = CODED ? (__any_sync(FULL, K != 0u) != 0) : true;  // can any lane's column hold a NaN?
+      uint32_t mnt = 0xffffffffu, mxb = 0u;
+      // (one gather per sample and lane; a full chunk keeps all 32 gathers of a lane in flight)
+      auto visit = [&](int32_t rj, int pos) {
+        if (CODED) {
+          const uint32_t b8 = act0 ? (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(col) + rj) : 0u;
+          s_x[pos * 32 + lane] = (VT)b8;
+          mxb = max(mxb, b8);
+          mnt = min(mnt, b8 - K);
+        } else {
+          const double x = act0 ? __ldg(reinterpret_cast<const double *>(col) + rj) : 0.0;
+          s_x[pos * 32 + lane] = (VT)x;
+          if (x < mn) mn = x;
+          if (x > mx) mx = x;
+          has_nan |= (x != x);
+        }
+      };
       for (int w = 0; w < nw; w++) {
         const int j0 = w << 5, cnt = min(32, n - j0);
         const int32_t row = (lane < cnt) ? idx[j0 + lane] : 0;
-#pragma unroll 8
-        for (int jj = 0; jj < cnt; jj++) {
-          const int32_t rj = __shfl_sync(FULL, row, jj);
-          if (CODED) {
-            const uint32_t b8 = act0 ? (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(col) + rj) : 0u;
-            s_x[(j0 + jj) * 32 + lane] = (VT)b8;
-            const uint32_t c8 = b8 + coff;  // wide code: 0 NaN, r + 1 for dict[r]
-            mnraw = min(mnraw, c8);
-            mxc = max(mxc, c8);
-            mnc = min(mnc, c8 - 1u);  // NaN (code 0) wraps to the top and never wins
-          } else {
-            const double x = act0 ? __ldg(reinterpret_cast<const double *>(col) + rj) : 0.0;
-            s_x[(j0 + jj) * 32 + lane] = (VT)x;
-            if (x < mn) mn = x;
-            if (x > mx) mx = x;
-            has_nan |= (x != x);
-          }
+        if (cnt == 32) {
+#pragma unroll
+          for (int jj = 0; jj < 32; jj++) visit(__shfl_sync(FULL, row, jj), j0 + jj);
+        } else {
+#pragma unroll 4
+          for (int jj = 0; jj < cnt; jj++) visit(__shfl_sync(FULL, row, jj), j0 + jj);
         }
       }
       uint32_t thr = 0u;
+      const uint32_t wmax = CODED ? ((K == 1u) ? mxb : mxb + 1u) : 0u;  // largest wide code; 0 = only NaNs
       if (CODED) {
-        has_nan = (mnraw == 0u);
-        if (act0 && mxc != 0u) {
+        if (act0 && wmax != 0u) {
           const double *dc8 = p.dict + (int64_t)f * 256;
-          mn = __ldg(dc8 + mnc);
-          mx = __ldg(dc8 + (mxc - 1u));
+          mn = __ldg(dc8 + mnt);
+          mx = __ldg(dc8 + (wmax - 1u));
         }
       }
-      const bool const0 = act0 && (mx <= mn) && !has_nan;  // pkg:236
+      // ---- pass 2: side bitmasks over the samples from the parked values.  The cutpoint only depends on
+      //      min / max (pkg:240); for byte codes the NaN samples are found here (has_nan = any NaN bit).
       const double cut = ET_ADD(mn, ET_MUL(ET_SUB(mx, mn), u));  // pkg:240
       if (CODED) {
-        if (act0 && !const0 && mxc != 0u) {
-          // thr = number of dictionary entries below the cutpoint; all of dict[0, mnc) are, none past mxc - 1
+        if (act0 && wmax != 0u && !(mx <= mn)) {
+          // thr = number of dictionary entries below the cutpoint; all of dict[0, mnt) are, none past wmax - 1
           const double *dc8 = p.dict + (int64_t)f * 256;
-          uint32_t lo = mnc, hi = mxc;
+          uint32_t lo = mnt, hi = wmax;
           while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
             if (__ldg(dc8 + mid) < cut)
@@ -1650,49 +1649,52 @@ __global__ void __launch_bounds__(32 * LANE_WARPS) k_lane(P p, int32_t qcount, i
           thr = lo;
         }
       }
-      // ---- pass 2: side bitmasks over the samples from the parked values
-      uint32_t lt[NW], nn[NW];
-#pragma unroll
-      for (int w = 0; w < NW; w++) {
-        lt[w] = 0u;
-        nn[w] = 0u;
-        if (w < nw) {
-          const int j0 = w << 5, cnt = min(32, n - j0);
+      for (int w = 0; w < nw; w++) {
+        const int j0 = w << 5, cnt = min(32, n - j0);
+        uint32_t lt = 0u, nn = 0u;
+        if (CODED) {
+          if (nan_cols) {
+#pragma unroll 8
+            for (int jj = 0; jj < cnt; jj++) {
+              const uint32_t t = (uint32_t)s_x[(j0 + jj) * 32 + lane] - K;
+              lt |= (uint32_t)(t < thr) << jj;
+              nn |= (uint32_t)(t == 0xffffffffu) << jj;
+            }
+          } else {
+#pragma unroll 8
+            for (int jj = 0; jj < cnt; jj++) lt |= (uint32_t)((uint32_t)s_x[(j0 + jj) * 32 + lane] < thr) << jj;
+          }
+        } else {
 #pragma unroll 8
           for (int jj = 0; jj < cnt; jj++) {
-            if (CODED) {
-              const uint32_t c8 = (uint32_t)s_x[(j0 + jj) * 32 + lane] + coff;
-              lt[w] |= (uint32_t)((c8 - 1u) < thr) << jj;
-              nn[w] |= (uint32_t)(c8 == 0u) << jj;
-            } else {
-              const double x = (double)s_x[(j0 + jj) * 32 + lane];
-              lt[w] |= (uint32_t)(x < cut) << jj;
-              nn[w] |= (uint32_t)(x != x) << jj;
-            }
+            const double x = (double)s_x[(j0 + jj) * 32 + lane];
+            lt |= (uint32_t)(x < cut) << jj;
+            nn |= (uint32_t)(x != x) << jj;
           }
         }
+        s_lt[w * 32 + lane] = lt;
+        s_nn[w * 32 + lane] = nn;
+        if (CODED) has_nan |= (nn != 0u);
       }
+      const bool const0 = act0 && (mx <= mn) && !has_nan;  // pkg:236
       // ---- exact score of this lane's candidate (pkg:250-275)
       double s = NAN;
       bool mil = false;
       if (act0 && !const0) {
         double sn, sl = NAN;
         if (TASK == TASK_CLS)
-          sn = gini_score_bits<NW>(lt, s_cm, s_hnode, C, n, nw, total);
+          sn = gini_score_bits(s_lt, s_nn, false, lane, s_cm, s_hnode, C, n, nw, NW, total);
         else if (TASK == TASK_REG)
-          sn = var_reduction_bits<NW>(lt, s_y, n, nw, total);
+          sn = var_reduction_bits(s_lt, s_nn, false, lane, s_y, n, nw, total);
         else
-          sn = gini_score_w_bits<NW>(lt, s_cm, s_y, C, n, nw, total, nsum);
+          sn = gini_score_w_bits(s_lt, s_nn, false, lane, s_cm, s_y, C, n, nw, NW, total, nsum);
         if (has_nan) {
-          uint32_t ln[NW];
-#pragma unroll
-          for (int w = 0; w < NW; w++) ln[w] = lt[w] | nn[w];
           if (TASK == TASK_CLS)
-            sl = gini_score_bits<NW>(ln, s_cm, s_hnode, C, n, nw, total);
+            sl = gini_score_bits(s_lt, s_nn, true, lane, s_cm, s_hnode, C, n, nw, NW, total);
           else if (TASK == TASK_REG)
-            sl = var_reduction_bits<NW>(ln, s_y, n, nw, total);
+            sl = var_reduction_bits(s_lt, s_nn, true, lane, s_y, n, nw, total);
           else
-            sl = gini_score_w_bits<NW>(ln, s_cm, s_y, C, n, nw, total, nsum);
+            sl = gini_score_w_bits(s_lt, s_nn, true, lane, s_cm, s_y, C, n, nw, NW, total, nsum);
         }
         mil = !(sl != sl) && (sl > sn || (sn != sn));  // pkg:272-275
         s = mil ? sl : sn;
@@ -1729,8 +1731,8 @@ __global__ void __launch_bounds__(32 * LANE_WARPS) k_lane(P p, int32_t qcount, i
         best_feature = __shfl_sync(FULL, f, bl);
         best_cut = __shfl_sync(FULL, cut, bl);
         best_mil = __shfl_sync(FULL, (int)mil, bl);
-#pragma unroll
-        for (int w = 0; w < NW; w++) best_mask[w] = __shfl_sync(FULL, mil ? (lt[w] | nn[w]) : lt[w], bl);
+        __syncwarp();
+        for (int w = lane; w < nw; w += 32) s_best[w] = s_lt[w * 32 + bl] | (best_mil ? s_nn[w * 32 + bl] : 0u);
       }
       if (!p.replay && (is_const || is_nan)) atomicOr(&s_const[f >> 5], 1u << (f & 31));
       visited += __popc(m_cnt);
@@ -1772,7 +1774,7 @@ __global__ void __launch_bounds__(32 * LANE_WARPS) k_lane(P p, int32_t qcount, i
     double *lv = p.o.leaf_vals + (int64_t)ls * lw;
     if (TASK == TASK_CLS) {
       const double inv = ET_DIV(1.0, (double)n);
-      for (int c = lane; c < C; c += 32) lv[c] = et_repeat_add(inv, s_hnode[c]);  // pkg:960-964
+      for (int c = lane; c < C; c += 32) lv[c] = repeat_add_dev(inv, s_hnode[c]);  // pkg:960-964
     } else if (TASK == TASK_CLSW) {
       for (int c = lane; c < C; c += 32) lv[c] = s_dist[c];
     } else {
@@ -1781,8 +1783,9 @@ __global__ void __launch_bounds__(32 * LANE_WARPS) k_lane(P p, int32_t qcount, i
     return;
   }
   int32_t nl = 0;
+  for (int w = lane; w < nw; w += 32) nl += __popc(s_best[w]);
 #pragma unroll
-  for (int w = 0; w < NW; w++) nl += __popc(best_mask[w]);
+  for (int o = 16; o > 0; o >>= 1) nl += __shfl_xor_sync(FULL, nl, o);
   int32_t slot = 0;
   if (lane == 0) {
     slot = atomicAdd(&p.cnt->next_f, 2);
@@ -1822,31 +1825,30 @@ __global__ void __launch_bounds__(32 * LANE_WARPS) k_lane(P p, int32_t qcount, i
   {
     int32_t lpos = b, rpos = b + nl;
     const uint32_t below = (1u << lane) - 1u;
-#pragma unroll
-    for (int w = 0; w < NW; w++) {
-      if (w < nw) {
-        const int j = w * 32 + lane;
-        const bool has = j < n;
-        const int cnt = min(32, n - w * 32);
-        const uint32_t valid = (cnt >= 32) ? FULL : ((1u << cnt) - 1u);
-        const uint32_t lm = best_mask[w] & valid, rm = ~best_mask[w] & valid;
-        if (has) {
-          const bool left = (lm >> lane) & 1u;
-          const int32_t dst = left ? lpos + __popc(lm & below) : rpos + __popc(rm & below);
-          p.idx_dst[base + dst] = idx[j];
-          if (TASK == TASK_REG) {
-            p.yr_dst[base + dst] = s_y[j];
-          } else {
-            p.yc_dst[base + dst] = p.yc_src[base + b + j];
-            if (TASK == TASK_CLSW) p.w_dst[base + dst] = s_y[j];
-          }
+    for (int w = 0; w < nw; w++) {
+      const int j = w * 32 + lane;
+      const bool has = j < n;
+      const int cnt = min(32, n - w * 32);
+      const uint32_t valid = (cnt >= 32) ? FULL : ((1u << cnt) - 1u);
+      const uint32_t bm = s_best[w];
+      const uint32_t lm = bm & valid, rm = ~bm & valid;
+      if (has) {
+        const bool left = (lm >> lane) & 1u;
+        const int32_t dst = left ? lpos + __popc(lm & below) : rpos + __popc(rm & below);
+        p.idx_dst[base + dst] = idx[j];
+        if (TASK == TASK_REG) {
+          p.yr_dst[base + dst] = s_y[j];
+        } else {
+          p.yc_dst[base + dst] = p.yc_src[base + b + j];
+          if (TASK == TASK_CLSW) p.w_dst[base + dst] = s_y[j];
         }
-        lpos += __popc(lm);
-        rpos += __popc(rm);
       }
+      lpos += __popc(lm);
+      rpos += __popc(rm);
     }
   }
 }
+#undef LANE_IN
 
 // ---- pool (creation order) -> per-tree pre-order ----------------------------------------------
 __global__ void k_subtree_sizes(Pool o, int32_t lo, int32_t hi, int32_t *size, int32_t *nleaf) {
@@ -1979,6 +1981,15 @@ namespace {
 
 struct PhaseTimer {
   bool on = getenv("ETGPU_TIMING") != nullptr;
+  bool per_level = on && atoi(getenv("ETGPU_TIMING")) >= 2;
+  double last[8] = {0};
+  void level_report(int level, const int32_t *qn) {
+    if (!per_level) return;
+    fprintf(stderr, "[etgpu level %3d] nodes n32=%d n64=%d n128=%d n256=%d n512=%d mid=%d cta=%d | ms tiny=%.3f warp=%.3f mid=%.3f cta=%.3f\n",
+            level, qn[0], qn[1], qn[2], qn[3], qn[4], qn[5], qn[6], acc[7] - last[7], acc[2] - last[2], acc[6] - last[6],
+            acc[3] - last[3]);
+    for (int i = 0; i < 8; i++) last[i] = acc[i];
+  }
   cudaStream_t st;
   double acc[8] = {0};
   std::chrono::steady_clock::time_point t0;
@@ -2035,17 +2046,13 @@ struct LevelCfg {
   bool coded;      // nodes of up to 512 samples: k_lane on byte codes
   bool coded_big;  // larger nodes: byte-coded CTA teams (unweighted classification, <= 32 classes)
   size_t smem_warp, smem_mid, smem_cta;  // k_node teams (per team)
-  size_t smem_lane[3];                   // k_lane per warp, classes 0..2
+  size_t smem_lane[5];                   // k_lane per warp, classes 0..4
 };
 
-template <int TASK, typename VT, int NW>
-void launch_lane(et_ctx *ctx, const P &p, int32_t count, int qi, size_t smem_per_warp, EventTimer &et) {
-  cudaStream_t st = ctx->stream;
-  int e0 = et.rec(st);
-  k_lane<TASK, VT, NW><<<(unsigned)ceil_div(count, LANE_WARPS), 32 * LANE_WARPS, smem_per_warp * LANE_WARPS, st>>>(
-      p, count, qi);
-  int e1 = et.rec(st);
-  et.spans[0].push_back({e0, e1});
+template <int TASK, typename VT>
+void launch_lane(et_ctx *ctx, const P &p, int32_t count, int qi, int NW, size_t smem_per_warp, cudaStream_t st) {
+  k_lane<TASK, VT><<<(unsigned)ceil_div(count, LANE_WARPS), 32 * LANE_WARPS, smem_per_warp * LANE_WARPS, st>>>(
+      p, count, qi, NW);
   ctx->launches++;
 }
 
@@ -2055,61 +2062,73 @@ void launch_coded_team(const P &p, int32_t count, int qi, size_t smem, cudaStrea
   if constexpr (TASK == TASK_CLS) k_node<TASK_CLS, TEAM, true><<<(unsigned)count, TEAM, smem, st>>>(p, count, qi);
 }
 
+// One level = one launch per non-empty size class.  The classes are independent (disjoint nodes), so
+// each runs on its own stream: the few long-running CTAs of the large nodes overlap with the many
+// small teams instead of serialising behind them.  (ETGPU_TIMING serialises them to time each.)
 template <int TASK>
 void launch_level(et_ctx *ctx, const P &p, const int32_t *qn, const LevelCfg &lc, PhaseTimer &pt, EventTimer &et) {
-  cudaStream_t st = ctx->stream;
-  // largest teams first: their CTAs run longest, the small-node kernels fill in behind them
-  if (qn[4] > 0) {
+  cudaStream_t main_st = ctx->stream;
+  const bool fork = !pt.on;
+  int used = 0;
+  for (int q = 0; q < NQ; q++) used += (qn[q] > 0);
+  const int e0 = et.rec(main_st);
+  if (fork && used > 1) cudaEventRecord(ctx->ev_fork, main_st);
+  bool joined[NQ] = {false};
+  int first = 1;
+  auto stream_for = [&](int side) -> cudaStream_t {
+    if (!fork || used <= 1 || first) {  // the first (largest) class stays on the main stream
+      first = 0;
+      return main_st;
+    }
+    cudaStreamWaitEvent(ctx->side[side], ctx->ev_fork, 0);
+    joined[side] = true;
+    return ctx->side[side];
+  };
+  // largest teams first: their CTAs run longest
+  if (qn[Q_CTA] > 0) {
     pt.start();
-    int e0 = et.rec(st);
+    cudaStream_t st = stream_for(Q_CTA);
     if (lc.coded_big)
-      launch_coded_team<TASK, CBIG_TEAM>(p, qn[4], 4, lc.smem_cta, st);
+      launch_coded_team<TASK, CBIG_TEAM>(p, qn[Q_CTA], Q_CTA, lc.smem_cta, st);
     else
-      k_node<TASK, CTA_TEAM, false><<<(unsigned)qn[4], CTA_TEAM, lc.smem_cta, st>>>(p, qn[4], 4);
-    int e1 = et.rec(st);
-    et.spans[1].push_back({e0, e1});
+      k_node<TASK, CTA_TEAM, false><<<(unsigned)qn[Q_CTA], CTA_TEAM, lc.smem_cta, st>>>(p, qn[Q_CTA], Q_CTA);
     ctx->launches++;
     pt.stop(3);
   }
-  if (qn[3] > 0) {
+  if (qn[Q_MID] > 0) {
     pt.start();
-    int e0 = et.rec(st);
+    cudaStream_t st = stream_for(Q_MID);
     if (lc.coded_big)
-      launch_coded_team<TASK, MID_TEAM>(p, qn[3], 3, lc.smem_mid, st);
+      launch_coded_team<TASK, MID_TEAM>(p, qn[Q_MID], Q_MID, lc.smem_mid, st);
     else
-      k_node<TASK, MID_TEAM, false><<<(unsigned)qn[3], MID_TEAM, lc.smem_mid, st>>>(p, qn[3], 3);
-    int e1 = et.rec(st);
-    et.spans[1].push_back({e0, e1});
+      k_node<TASK, MID_TEAM, false><<<(unsigned)qn[Q_MID], MID_TEAM, lc.smem_mid, st>>>(p, qn[Q_MID], Q_MID);
     ctx->launches++;
     pt.stop(6);
   }
-  if (qn[2] > 0) {
+  for (int q = Q_WARP; q >= 0; q--) {
+    if (qn[q] <= 0) continue;
     pt.start();
+    cudaStream_t st = stream_for(q);
     if (lc.coded) {
-      launch_lane<TASK, uint8_t, 16>(ctx, p, qn[2], 2, lc.smem_lane[2], et);
-    } else {
-      int e0 = et.rec(st);
+      launch_lane<TASK, uint8_t>(ctx, p, qn[q], q, 1 << q, lc.smem_lane[q], st);
+    } else if (q == 0) {
+      launch_lane<TASK, double>(ctx, p, qn[q], q, 1, lc.smem_lane[0], st);
+    } else {  // FP64 tables: only class Q_WARP is populated besides class 0
       k_node<TASK, 32, false>
-          <<<(unsigned)ceil_div(qn[2], WARPS_PER_CTA), 32 * WARPS_PER_CTA, lc.smem_warp * WARPS_PER_CTA, st>>>(p, qn[2], 2);
-      int e1 = et.rec(st);
-      et.spans[0].push_back({e0, e1});
+          <<<(unsigned)ceil_div(qn[q], WARPS_PER_CTA), 32 * WARPS_PER_CTA, lc.smem_warp * WARPS_PER_CTA, st>>>(p, qn[q], q);
       ctx->launches++;
     }
-    pt.stop(2);
+    pt.stop(q == 0 ? 7 : 2);
   }
-  if (qn[1] > 0) {  // byte-coded tables only
-    pt.start();
-    launch_lane<TASK, uint8_t, 4>(ctx, p, qn[1], 1, lc.smem_lane[1], et);
-    pt.stop(2);
+  for (int i = 0; i < NQ; i++) {
+    if (joined[i]) {
+      cudaEventRecord(ctx->ev_join[i], ctx->side[i]);
+      cudaStreamWaitEvent(main_st, ctx->ev_join[i], 0);
+    }
   }
-  if (qn[0] > 0) {
-    pt.start();
-    if (lc.coded)
-      launch_lane<TASK, uint8_t, 1>(ctx, p, qn[0], 0, lc.smem_lane[0], et);
-    else
-      launch_lane<TASK, double, 1>(ctx, p, qn[0], 0, lc.smem_lane[0], et);
-    pt.stop(7);
-  }
+  const int e1 = et.rec(main_st);
+  et.spans[0].push_back({e0, e1});
+  if (qn[Q_MID] + qn[Q_CTA] > 0) et.spans[1].push_back({e0, e1});
 }
 
 template <int TASK>
@@ -2128,14 +2147,10 @@ void set_smem_attr(const LevelCfg &lc) {
                                     (int)lc.smem_cta));
   }
   if (lc.coded) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, uint8_t, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(lc.smem_lane[0] * LANE_WARPS)));
-    CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, uint8_t, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(lc.smem_lane[1] * LANE_WARPS)));
-    CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, uint8_t, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(lc.smem_lane[2] * LANE_WARPS)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(lc.smem_lane[4] * LANE_WARPS)));
   } else {
-    CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(lc.smem_lane[0] * LANE_WARPS)));
     CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(lc.smem_warp * WARPS_PER_CTA)));
@@ -2182,10 +2197,8 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
   lc.smem_warp = (size_t)lay_w.bytes;
   lc.smem_mid = (size_t)lay_m.bytes;
   lc.smem_cta = (size_t)lay_c.bytes;
-  lc.smem_lane[0] = (size_t)lane_smem_bytes(task, C, W, replay, 1, lc.coded ? 1 : 8);
-  lc.smem_lane[1] = (size_t)lane_smem_bytes(task, C, W, replay, 4, 1);
-  lc.smem_lane[2] = (size_t)lane_smem_bytes(task, C, W, replay, 16, 1);
-  if (lc.coded && lc.smem_lane[2] * LANE_WARPS > 200 * 1024) lc.coded = false;  // (hundreds of classes)
+  for (int q = 0; q < 5; q++) lc.smem_lane[q] = (size_t)lane_smem_bytes(task, C, W, replay, 1 << q, 1);
+  if (lc.coded && lc.smem_lane[4] * LANE_WARPS > 200 * 1024) lc.coded = false;  // (hundreds of classes)
   lc.coded_big = lc.coded && task == TASK_CLS && C <= 32;
   if (lc.coded_big) {
     lc.smem_mid = (size_t)make_lay(task, MID_TEAM, C, NB, W, replay, true).bytes;
@@ -2315,9 +2328,9 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       p.dict = D->dict;
       p.coff = D->coff;
       p.cls_max[0] = NT_MAX;
-      p.cls_max[1] = lc.coded ? 128 : NT_MAX;
-      p.cls_max[2] = NW_MAX;
-      p.cls_max[3] = NM_MAX;
+      for (int q = 1; q < Q_WARP; q++) p.cls_max[q] = lc.coded ? (NT_MAX << q) : NT_MAX;
+      p.cls_max[Q_WARP] = NW_MAX;
+      p.cls_max[Q_MID] = NM_MAX;
       p.tr = Trace{d_tr_cand_begin, d_tr_cand_count, d_tr_left, d_tr_right, d_tr_cand_feature, d_tr_cand_u,
                    d_tr_cand_flag};
       int srcb = 0, cl = 0;
@@ -2348,7 +2361,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
 
       int64_t n_nodes = Bt, n_leaves = 0;
       std::vector<int32_t> level_start{0};
-      int32_t qn[NQ] = {0, 0, 0, 0, 0};
+      int32_t qn[NQ] = {0};
       qn[size_class(p, n)] = Bt;
       Counters hc;
       memset(&hc, 0, sizeof(hc));
@@ -2358,8 +2371,8 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
         ws.fr[cl ^ 1].ensure((size_t)F * 2, C, W, task == TASK_CLS, !replay);
         for (int q = 0; q < NQ; q++) ws.q[cl ^ 1][q].ensure((size_t)F * 2, 1.5);
         ws.pool.grow((size_t)(n_nodes + 2 * (int64_t)F), (size_t)n_nodes, (size_t)(n_leaves + F), (size_t)n_leaves, lw, st);
-        if (task != TASK_CLS && qn[3] + qn[4] > 0)
-          ws.scratch.ensure((size_t)NB * 2 * ((size_t)Bt * (size_t)n / 32 + (size_t)(qn[3] + qn[4]) + 1) + 64, 1.0);
+        if (task != TASK_CLS && qn[Q_MID] + qn[Q_CTA] > 0)
+          ws.scratch.ensure((size_t)NB * 2 * ((size_t)Bt * (size_t)n / 32 + (size_t)(qn[Q_MID] + qn[Q_CTA]) + 1) + 64, 1.0);
         pt.stop(0);
         p.idx_src = ws.idx[srcb].p;
         p.idx_dst = ws.idx[srcb ^ 1].p;
@@ -2384,6 +2397,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
           launch_level<TASK_CLSW>(ctx, p, qn, lc, pt, evt);
         else
           launch_level<TASK_REG>(ctx, p, qn, lc, pt, evt);
+        pt.level_report((int)S.levels - 1, qn);
         pt.start();
         CUDA_CHECK(cudaMemcpyAsync(&hc, ws.cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         // the next level starts from clean per-level counters (leaf count and stats keep accumulating)
@@ -2498,8 +2512,8 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
     S.gpu_ms = ms;
-    S.gpu_ms_split = tacc[0] + tacc[1];  // node kernels: split search + partition fused
-    S.gpu_ms_partition = tacc[1];        // of which CTA-owned (large) nodes
+    S.gpu_ms_split = tacc[0];      // node kernels (split search + partition fused), all size classes of a level overlapped
+    S.gpu_ms_partition = tacc[1];  // ... of which levels that still hold CTA-owned (large) nodes
     S.launches = ctx->launches - launches0;
     pt.report();
   } catch (...) {

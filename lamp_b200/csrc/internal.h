@@ -12,6 +12,9 @@ struct et_ctx {
   std::mutex mu;  // a context serialises its calls
   int64_t launches = 0;
   Workspace *ws = nullptr;
+  // side streams: the node kernels of one level (one launch per size class) run concurrently
+  cudaStream_t side[7] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[7] = {};
 };
 void et_workspace_free(Workspace *ws);
 
