@@ -150,6 +150,18 @@ int et_forest_import(et_ctx *ctx, int32_t m, int32_t leaf_width, int32_t is_regr
                      const int32_t *tree_sizes, const int32_t *feature, const double *cut,
                      const uint8_t *missing_is_less, const int32_t *left, const int32_t *right,
                      const double *leaf_values, et_forest **out);
+/* Packed serialized forest = the device layout itself, copied device->host without any per-node
+ * work (the caller's buffers may be pinned): `nodes` holds total_nodes records of 16 bytes
+ *     { double cutpoint; int32 feature | (splitMissingIsLess << 30), -1 for a leaf;
+ *       int32 right child (tree-local pre-order id; the left child is node + 1) | forest-wide leaf index }
+ * for all trees concatenated in tree order, each tree in pre-order; `leaves` holds total_leaves x
+ * leaf_width doubles (leaf values in pre-order); `tree_off` holds m + 1 node offsets.  This is the
+ * persisted / gathered form of Seq[ClassificationTree] / Seq[RegressionTree] (extratrees.scala:3-63). */
+int et_forest_packed_dims(const et_forest *f, int64_t *total_nodes, int64_t *total_leaves);
+int et_forest_export_packed(et_forest *f, void *nodes_out, double *leaves_out, int64_t *tree_off_out);
+int et_forest_import_packed(et_ctx *ctx, int32_t m, int32_t leaf_width, int32_t is_regression,
+                            int64_t total_nodes, int64_t total_leaves, const void *nodes,
+                            const double *leaves, const int64_t *tree_off, et_forest **out);
 void et_forest_free(et_forest *f);
 
 /* ---- predict -------------------------------------------------------------------------------

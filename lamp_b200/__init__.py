@@ -5,3 +5,4 @@ binding, the host-side mirror of the reference's public API, and tree sharding a
 from .extratrees import (ClassificationLeaf, ClassificationNonLeaf, Context, DeviceData, FlatTree, Forest,  # noqa: F401
                          RegressionLeaf, RegressionNonLeaf, buildForestClassification, buildForestRegression,
                          default_context, make_replay, predictClassification, predictRegression)
+from ._capi import EtError  # noqa: F401

@@ -67,6 +67,10 @@ SIGNATURES = {
     "et_forest_export": (C.c_int, [vp, C.c_int32, ip, dp, bp, ip, ip, dp]),
     "et_forest_export_all": (C.c_int, [vp, ip, ip, dp, bp, ip, ip, dp]),
     "et_forest_import": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, ip, ip, dp, bp, ip, ip, dp, C.POINTER(vp)]),
+    "et_forest_packed_dims": (C.c_int, [vp, lp, lp]),
+    "et_forest_export_packed": (C.c_int, [vp, vp, vp, vp]),
+    "et_forest_import_packed": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, vp, vp, vp,
+                                          C.POINTER(vp)]),
     "et_forest_free": (None, [vp]),
     "et_predict_classification": (C.c_int, [vp, vp, dp, C.c_int64, C.c_int32, dp, C.c_int32]),
     "et_predict_regression": (C.c_int, [vp, vp, dp, C.c_int64, C.c_int32, dp, C.c_int32]),

@@ -31,6 +31,59 @@ extern "C" int32_t et_abi_version(void) { return ET_ABI_VERSION; }
 extern "C" const char *et_last_error(void) { return g_last_error.c_str(); }
 extern "C" double et_debug_repeat_add(double c, int64_t h) { return et_repeat_add(c, h); }
 
+// ---- device block cache ----------------------------------------------------------------------
+// sizes are rounded up to 8 classes per octave, so blocks of similar size (forests of consecutive builds)
+// are interchangeable
+static size_t block_class(size_t bytes) {
+  bytes = std::max<size_t>(bytes, 256);
+  if (bytes <= ((size_t)1 << 20)) return (bytes + 255) / 256 * 256;
+  int lg = 63 - __builtin_clzll((unsigned long long)bytes);
+  const size_t step = (size_t)1 << (lg - 3);
+  return (bytes + step - 1) / step * step;
+}
+
+void *et_dev_alloc(et_ctx *ctx, size_t bytes) {
+  bytes = block_class(bytes);
+  for (size_t i = 0; i < ctx->cache.size(); i++) {
+    if (ctx->cache[i].bytes == bytes) {
+      void *p = ctx->cache[i].p;
+      ctx->cache_bytes -= bytes;
+      ctx->cache.erase(ctx->cache.begin() + (long)i);
+      return p;
+    }
+  }
+  void *p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    // give the cached blocks back and retry once
+    for (auto &b : ctx->cache) cudaFree(b.p);
+    ctx->cache.clear();
+    ctx->cache_bytes = 0;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+  }
+  return p;
+}
+
+void et_dev_free(et_ctx *ctx, void *p, size_t bytes) {
+  if (!p) return;
+  bytes = block_class(bytes);
+  const size_t kMaxBlocks = 16, kMaxBytes = (size_t)8 << 30;
+  if (!ctx || bytes > kMaxBytes) {
+    cudaFree(p);
+    return;
+  }
+  while (!ctx->cache.empty() && (ctx->cache.size() >= kMaxBlocks || ctx->cache_bytes + bytes > kMaxBytes)) {
+    cudaFree(ctx->cache.front().p);  // oldest first
+    ctx->cache_bytes -= ctx->cache.front().bytes;
+    ctx->cache.erase(ctx->cache.begin());
+  }
+  ctx->cache.push_back({p, bytes});
+  ctx->cache_bytes += bytes;
+}
+
 // ---- context --------------------------------------------------------------------------------
 extern "C" int et_init(int32_t device, et_ctx **out) {
   ET_API_BEGIN
@@ -74,13 +127,14 @@ extern "C" void et_shutdown(et_ctx *ctx) {
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   et_workspace_free(ctx->ws);
+  for (auto &b : ctx->cache) cudaFree(b.p);
   delete ctx;
 }
 
 extern "C" int et_set_stream(et_ctx *ctx, void *cuda_stream) {
   ET_API_BEGIN
   if (!ctx) ET_FAIL(ET_EINVAL, "et_set_stream: ctx is NULL");
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   ET_API_END
 }
@@ -133,9 +187,9 @@ static et_data *data_alloc(et_ctx *ctx, int64_t n, int32_t d) {
   D->d = d;
   D->ld = ((n + 15) / 16) * 16;
   size_t bytes = (size_t)std::max<int64_t>(D->ld, 16) * (size_t)std::max(d, 1) * sizeof(double);
-  cudaError_t e = cudaMalloc((void **)&D->x, bytes);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
+  D->x = static_cast<double *>(et_dev_alloc(ctx, bytes));
+  D->x_bytes = bytes;
+  if (!D->x) {
     delete D;
     ET_FAIL(ET_ENOMEM, "cannot allocate %zu bytes of HBM for the %lld x %d table", bytes, (long long)n, d);
   }
@@ -145,7 +199,7 @@ static et_data *data_alloc(et_ctx *ctx, int64_t n, int32_t d) {
 extern "C" int et_data_dense_alloc(et_ctx *ctx, int64_t n, int32_t d, et_data **out) {
   ET_API_BEGIN
   if (!ctx || !out) ET_FAIL(ET_EINVAL, "et_data_dense_alloc: NULL argument");
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   *out = data_alloc(ctx, n, d);
   ET_API_END
@@ -157,7 +211,7 @@ extern "C" int et_data_dense_colblock(et_ctx *ctx, et_data *D, const double *col
   if (!ctx || !D || (!cols && n_cols > 0)) ET_FAIL(ET_EINVAL, "et_data_dense_colblock: NULL argument");
   if (first_col < 0 || n_cols < 0 || first_col + n_cols > D->d)
     ET_FAIL(ET_EINVAL, "et_data_dense_colblock: columns [%d,%d) outside [0,%d)", first_col, first_col + n_cols, D->d);
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   if (n_cols > 0 && D->n > 0)
     CUDA_CHECK(cudaMemcpy2DAsync(D->x + (int64_t)first_col * D->ld, (size_t)D->ld * sizeof(double), cols,
@@ -165,12 +219,7 @@ extern "C" int et_data_dense_colblock(et_ctx *ctx, et_data *D, const double *col
                                  cudaMemcpyHostToDevice, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   if (D->coded != 0) {  // the coded copy is rebuilt at the next build
-    if (D->c8) cudaFree(D->c8);
-    if (D->dict) cudaFree(D->dict);
-    if (D->coff) cudaFree(D->coff);
-    D->c8 = nullptr;
-    D->dict = nullptr;
-    D->coff = nullptr;
+    et_data_drop_codes(D);
     D->coded = 0;
   }
   ET_API_END
@@ -179,17 +228,16 @@ extern "C" int et_data_dense_colblock(et_ctx *ctx, et_data *D, const double *col
 extern "C" int et_data_dense_rowmajor(et_ctx *ctx, const double *x, int64_t n, int32_t d, et_data **out) {
   ET_API_BEGIN
   if (!ctx || !out || (!x && n > 0 && d > 0)) ET_FAIL(ET_EINVAL, "et_data_dense_rowmajor: NULL argument");
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   et_data *D = data_alloc(ctx, n, d);
   if (n > 0 && d > 0) {
     // staged in row chunks of <= 256 MB so the temporary stays small next to the table
     int64_t chunk = std::max<int64_t>(1, ((int64_t)256 << 20) / ((int64_t)d * 8));
     chunk = std::min(chunk, n);
-    double *stage = nullptr;
-    cudaError_t e = cudaMalloc((void **)&stage, (size_t)chunk * d * sizeof(double));
-    if (e != cudaSuccess) {
-      cudaGetLastError();
+    const size_t stage_bytes = (size_t)chunk * d * sizeof(double);
+    double *stage = static_cast<double *>(et_dev_alloc(ctx, stage_bytes));
+    if (!stage) {
       et_data_free(D);
       ET_FAIL(ET_ENOMEM, "cannot allocate the upload staging buffer");
     }
@@ -203,11 +251,11 @@ extern "C" int et_data_dense_rowmajor(et_ctx *ctx, const double *x, int64_t n, i
       et_data_encode(ctx, D);
       CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     } catch (...) {
-      cudaFree(stage);
+      et_dev_free(ctx, stage, stage_bytes);
       et_data_free(D);
       throw;
     }
-    cudaFree(stage);
+    et_dev_free(ctx, stage, stage_bytes);
   }
   *out = D;
   ET_API_END
@@ -217,7 +265,7 @@ extern "C" int et_data_dense_rowmajor_device(et_ctx *ctx, const double *x_dev, i
                                              et_data **out) {
   ET_API_BEGIN
   if (!ctx || !out || (!x_dev && n > 0 && d > 0)) ET_FAIL(ET_EINVAL, "et_data_dense_rowmajor_device: NULL argument");
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   et_data *D = data_alloc(ctx, n, d);
   try {
@@ -265,7 +313,7 @@ extern "C" int et_data_set_target_classification(et_ctx *ctx, et_data *D, const 
               (long long)i, y[i], num_classes);
     hist[(size_t)y[i]]++;
   }
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   upload_vec(ctx, &D->y_cls, y, n_target);
   D->num_classes = num_classes;
@@ -279,7 +327,7 @@ extern "C" int et_data_set_target_regression(et_ctx *ctx, et_data *D, const doub
   if (n_target != D->n)
     ET_FAIL(ET_EINVAL, "requirement failed: Data.numRows(%lld) != target.length (%lld)", (long long)D->n,
             (long long)n_target);
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   upload_vec(ctx, &D->y_reg, y, n_target);
   ET_API_END
@@ -288,7 +336,7 @@ extern "C" int et_data_set_target_regression(et_ctx *ctx, et_data *D, const doub
 extern "C" int et_data_set_weights(et_ctx *ctx, et_data *D, const double *w, int64_t n_weights) {
   ET_API_BEGIN
   if (!ctx || !D) ET_FAIL(ET_EINVAL, "et_data_set_weights: NULL argument");
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   if (!w) {
     if (D->w) cudaFree(D->w);
@@ -316,10 +364,10 @@ extern "C" int et_data_dims(const et_data *D, int64_t *n, int32_t *d) {
 extern "C" void et_data_free(et_data *D) {
   if (!D) return;
   if (D->ctx) cudaSetDevice(D->ctx->device);
-  if (D->x) cudaFree(D->x);
-  if (D->c8) cudaFree(D->c8);
-  if (D->dict) cudaFree(D->dict);
-  if (D->coff) cudaFree(D->coff);
+  std::unique_lock<std::recursive_mutex> lk;
+  if (D->ctx) lk = std::unique_lock<std::recursive_mutex>(D->ctx->mu);
+  et_dev_free(D->ctx, D->x, D->x_bytes);
+  et_data_drop_codes(D);
   if (D->y_cls) cudaFree(D->y_cls);
   if (D->y_reg) cudaFree(D->y_reg);
   if (D->w) cudaFree(D->w);
@@ -351,7 +399,7 @@ extern "C" int et_build_classification(et_ctx *ctx, et_data *D, const int32_t *t
   if (!D->y_cls) ET_FAIL(ET_EINVAL, "build: no classification target attached");
   if (D->num_classes != num_classes) ET_FAIL(ET_EINVAL, "build: numClasses differs from the attached target's");
   if (D->n == 0 && m > 0) ET_FAIL(ET_EINVAL, "build: empty table (the reference fails on targetInSubset.raw(0))");
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   BuildArgs a;
   a.task = D->w ? 1 : 0;
@@ -392,7 +440,7 @@ extern "C" int et_build_regression(et_ctx *ctx, et_data *D, const double *target
   }
   if (!D->y_reg) ET_FAIL(ET_EINVAL, "build: no regression target attached");
   if (D->n == 0 && m > 0) ET_FAIL(ET_EINVAL, "requirement failed (subset.length > 0, pkg:779)");
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   BuildArgs a;
   a.task = 2;
@@ -425,8 +473,16 @@ extern "C" int et_build_regression(et_ctx *ctx, et_data *D, const double *target
 et_forest::~et_forest() {
   if (ctx) cudaSetDevice(ctx->device);
   if (d_tree_off) cudaFree(d_tree_off);
-  if (d_nodes) cudaFree(d_nodes);
-  if (d_leaf) cudaFree(d_leaf);
+  std::unique_lock<std::recursive_mutex> lk;
+  if (ctx) lk = std::unique_lock<std::recursive_mutex>(ctx->mu);
+  if (nodes_bytes)
+    et_dev_free(ctx, d_nodes, nodes_bytes);
+  else if (d_nodes)
+    cudaFree(d_nodes);
+  if (leaf_bytes)
+    et_dev_free(ctx, d_leaf, leaf_bytes);
+  else if (d_leaf)
+    cudaFree(d_leaf);
 }
 
 extern "C" void et_forest_free(et_forest *f) { delete f; }
@@ -434,7 +490,7 @@ extern "C" void et_forest_free(et_forest *f) { delete f; }
 // The forest lives in HBM; the host copy is fetched on first export.
 void et_forest_fetch(et_forest *f) {
   if (f->host_ready) return;
-  std::lock_guard<std::mutex> lk(f->ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(f->ctx->mu);
   if (f->host_ready) return;
   CUDA_CHECK(cudaSetDevice(f->ctx->device));
   f->h_nodes.resize((size_t)f->total_nodes);
@@ -567,7 +623,7 @@ extern "C" int et_forest_import(et_ctx *ctx, int32_t m, int32_t leaf_width, int3
   }
   f->total_leaves = n_leaves;
   f->host_ready = true;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   CUDA_CHECK(cudaMalloc((void **)&f->d_tree_off, ((size_t)m + 1) * sizeof(int64_t)));
   CUDA_CHECK(cudaMalloc((void **)&f->d_nodes, std::max<size_t>(1, (size_t)f->total_nodes) * sizeof(PNode)));
@@ -586,24 +642,100 @@ extern "C" int et_forest_import(et_ctx *ctx, int32_t m, int32_t leaf_width, int3
   ET_API_END
 }
 
+// ---- packed (device-layout) serialization ----------------------------------------------------
+extern "C" int et_forest_packed_dims(const et_forest *f, int64_t *total_nodes, int64_t *total_leaves) {
+  if (!f) {
+    et_set_error("et_forest_packed_dims: NULL forest");
+    return ET_EINVAL;
+  }
+  if (total_nodes) *total_nodes = f->total_nodes;
+  if (total_leaves) *total_leaves = f->total_leaves;
+  return ET_OK;
+}
+
+extern "C" int et_forest_export_packed(et_forest *f, void *nodes_out, double *leaves_out, int64_t *tree_off_out) {
+  ET_API_BEGIN
+  if (!f || !nodes_out || !leaves_out || !tree_off_out) ET_FAIL(ET_EINVAL, "et_forest_export_packed: NULL argument");
+  std::lock_guard<std::recursive_mutex> lk(f->ctx->mu);
+  CUDA_CHECK(cudaSetDevice(f->ctx->device));
+  cudaStream_t st = f->ctx->stream;
+  if (f->total_nodes)
+    CUDA_CHECK(cudaMemcpyAsync(nodes_out, f->d_nodes, (size_t)f->total_nodes * sizeof(PNode), cudaMemcpyDeviceToHost, st));
+  if (f->total_leaves)
+    CUDA_CHECK(cudaMemcpyAsync(leaves_out, f->d_leaf, (size_t)f->total_leaves * (size_t)f->leaf_width * sizeof(double),
+                               cudaMemcpyDeviceToHost, st));
+  for (int32_t t = 0; t <= f->m; t++) tree_off_out[t] = f->tree_off[(size_t)t];
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  ET_API_END
+}
+
+extern "C" int et_forest_import_packed(et_ctx *ctx, int32_t m, int32_t leaf_width, int32_t is_regression,
+                                       int64_t total_nodes, int64_t total_leaves, const void *nodes,
+                                       const double *leaves, const int64_t *tree_off, et_forest **out) {
+  ET_API_BEGIN
+  if (!ctx || !out || m < 0 || leaf_width <= 0 || total_nodes < 0 || total_leaves < 0 || !tree_off)
+    ET_FAIL(ET_EINVAL, "et_forest_import_packed: bad argument");
+  if ((total_nodes > 0 && !nodes) || (total_leaves > 0 && !leaves))
+    ET_FAIL(ET_EINVAL, "et_forest_import_packed: NULL array");
+  if (tree_off[0] != 0 || tree_off[m] != total_nodes) ET_FAIL(ET_EINVAL, "et_forest_import_packed: bad tree offsets");
+  const PNode *pn = static_cast<const PNode *>(nodes);
+  for (int32_t t = 0; t < m; t++) {
+    const int64_t off = tree_off[t], n = tree_off[t + 1] - off;
+    if (n <= 0) ET_FAIL(ET_EINVAL, "et_forest_import_packed: tree %d is empty", t);
+    for (int64_t i = 0; i < n; i++) {
+      const PNode &q = pn[off + i];
+      if (q.feat >= 0) {
+        if (q.right_or_leaf <= i + 1 || q.right_or_leaf >= n)
+          ET_FAIL(ET_EINVAL, "et_forest_import_packed: tree %d node %lld is not in pre-order", t, (long long)i);
+      } else if (q.right_or_leaf < 0 || q.right_or_leaf >= total_leaves) {
+        ET_FAIL(ET_EINVAL, "et_forest_import_packed: tree %d node %lld: leaf index out of range", t, (long long)i);
+      }
+    }
+  }
+  std::unique_ptr<et_forest> f(new et_forest());
+  f->ctx = ctx;
+  f->leaf_width = leaf_width;
+  f->is_regression = is_regression;
+  f->m = m;
+  f->tree_off.assign(tree_off, tree_off + m + 1);
+  f->total_nodes = total_nodes;
+  f->total_leaves = total_leaves;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  CUDA_CHECK(cudaMalloc((void **)&f->d_tree_off, ((size_t)m + 1) * sizeof(int64_t)));
+  CUDA_CHECK(cudaMalloc((void **)&f->d_nodes, std::max<size_t>(1, (size_t)total_nodes) * sizeof(PNode)));
+  CUDA_CHECK(cudaMalloc((void **)&f->d_leaf, std::max<size_t>(1, (size_t)total_leaves * leaf_width) * sizeof(double)));
+  cudaStream_t st = ctx->stream;
+  CUDA_CHECK(cudaMemcpyAsync(f->d_tree_off, tree_off, ((size_t)m + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  if (total_nodes)
+    CUDA_CHECK(cudaMemcpyAsync(f->d_nodes, nodes, (size_t)total_nodes * sizeof(PNode), cudaMemcpyHostToDevice, st));
+  if (total_leaves)
+    CUDA_CHECK(cudaMemcpyAsync(f->d_leaf, leaves, (size_t)total_leaves * leaf_width * sizeof(double),
+                               cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  *out = f.release();
+  ET_API_END
+}
+
 // ---- predict --------------------------------------------------------------------------------
 static void predict_host(et_ctx *ctx, et_forest *f, const double *x, int64_t n, int32_t d, double *out,
                          int sum_only, int want_regression) {
   if (!ctx || !f || (!x && n > 0 && d > 0) || (!out && n > 0)) ET_FAIL(ET_EINVAL, "predict: NULL argument");
   if (f->is_regression != want_regression) ET_FAIL(ET_EINVAL, "predict: forest kind does not match the call");
   if (n < 0 || d < 0) ET_FAIL(ET_EINVAL, "predict: negative dimensions");
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   if (n == 0) return;
   int lw = f->leaf_width;
   // rows are streamed through the GPU in chunks: H2D, traverse, D2H
   int64_t chunk = std::max<int64_t>(1, ((int64_t)512 << 20) / ((int64_t)std::max(d, 1) * 8));
   chunk = std::min(chunk, n);
-  double *dx = nullptr, *dout = nullptr;
-  if (cudaMalloc((void **)&dx, (size_t)chunk * std::max(d, 1) * sizeof(double)) != cudaSuccess ||
-      cudaMalloc((void **)&dout, (size_t)chunk * lw * sizeof(double)) != cudaSuccess) {
-    cudaGetLastError();
-    if (dx) cudaFree(dx);
+  const size_t dx_bytes = (size_t)chunk * std::max(d, 1) * sizeof(double), dout_bytes = (size_t)chunk * lw * sizeof(double);
+  double *dx = static_cast<double *>(et_dev_alloc(ctx, dx_bytes));
+  double *dout = static_cast<double *>(et_dev_alloc(ctx, dout_bytes));
+  if (!dx || !dout) {
+    et_dev_free(ctx, dx, dx_bytes);
+    et_dev_free(ctx, dout, dout_bytes);
     ET_FAIL(ET_ENOMEM, "predict: cannot allocate staging buffers");
   }
   try {
@@ -618,12 +750,12 @@ static void predict_host(et_ctx *ctx, et_forest *f, const double *x, int64_t n, 
       CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     }
   } catch (...) {
-    cudaFree(dx);
-    cudaFree(dout);
+    et_dev_free(ctx, dx, dx_bytes);
+    et_dev_free(ctx, dout, dout_bytes);
     throw;
   }
-  cudaFree(dx);
-  cudaFree(dout);
+  et_dev_free(ctx, dx, dx_bytes);
+  et_dev_free(ctx, dout, dout_bytes);
 }
 
 extern "C" int et_predict_classification(et_ctx *ctx, et_forest *f, const double *x, int64_t n, int32_t d,
@@ -643,7 +775,7 @@ static void predict_dev(et_ctx *ctx, et_forest *f, const double *x, int64_t n, i
                         int want_regression) {
   if (!ctx || !f || (!x && n > 0 && d > 0) || (!out && n > 0)) ET_FAIL(ET_EINVAL, "predict: NULL argument");
   if (f->is_regression != want_regression) ET_FAIL(ET_EINVAL, "predict: forest kind does not match the call");
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   if (n <= 0) return;
   et_predict_device_impl(ctx, f, x, n, d, out, sum_only);

@@ -94,6 +94,7 @@ struct Lay {
   int o_feat, o_flags, o_nleft, o_hnode, o_besthl, o_hist, o_redi, o_mask, o_bits, o_misc;  // int32
   int o_rows, o_lab, o_cm, o_ord;
   int o_coloff, o_cred, o_cb, o_thr;  // byte-coded CTA teams: column offsets, reduction scratch, per-candidate bytes
+  int o_park;                         // ... and (128-thread teams) the parked bytes of the node [sample][32 candidates]
   int hs;      // stride of one candidate's histogram row (odd: conflict-free per-candidate reads)
   int use_cm;  // warp teams: per-chunk class bitmasks fit in shared memory
   int bytes;
@@ -105,6 +106,8 @@ __host__ __device__ inline Lay make_lay(int task, int team, int C, int NB, int W
   int o = 0;  // in 8-byte units first
   L.o_coloff = o;
   o += coded ? 32 : 0;
+  L.o_park = o;  // 16-byte aligned: o counts 8-byte units and everything before is a multiple of 2
+  o += 0;  // (measured: parking costs more occupancy than the second gather pass costs time; kept switchable)
   L.o_u = o;
   o += NB;
   L.o_cut = o;
@@ -427,6 +430,133 @@ __device__ __forceinline__ int32_t rank_select_clear_fast(const uint32_t *taken,
 }
 
 
+// ---- byte-coded CTA teams: the two streaming passes over a node's samples ----------------------
+// NG = groups of 4 candidates read per sample (the batch holds up to 4 * NG candidates).  The loops carry
+// no branch, so all 4 * NG byte loads of a sample are in flight together.
+template <int NG>
+__device__ __forceinline__ void coded_load(const uint8_t *__restrict__ C8, const int64_t *s_coloff, int64_t r,
+                                           uint32_t (&b4)[NG]) {
+  uint32_t b[4 * NG];
+#pragma unroll
+  for (int c = 0; c < 4 * NG; c++) b[c] = __ldg(C8 + s_coloff[c] + r);
+#pragma unroll
+  for (int g = 0; g < NG; g++) b4[g] = b[4 * g] | (b[4 * g + 1] << 8) | (b[4 * g + 2] << 16) | (b[4 * g + 3] << 24);
+}
+
+// pass 1: per-candidate min of (byte - K), max of byte, min of byte, packed 4 candidates per register
+// (s_park != null: the packed bytes of every sample are parked in shared memory [sample][NG] for pass 2)
+template <int NG, int TEAM>
+__device__ __forceinline__ void coded_pass1(const uint8_t *__restrict__ C8, const int64_t *s_coloff,
+                                            const uint32_t *s_K4, const int32_t *rr, int32_t n, int tid,
+                                            uint32_t *s_cred, int wit, int lane, uint32_t *s_park) {
+  uint32_t mnT[NG], mxB[NG], mnB[NG], K4[NG];
+#pragma unroll
+  for (int g = 0; g < NG; g++) {
+    mnT[g] = 0xffffffffu;
+    mxB[g] = 0u;
+    mnB[g] = 0xffffffffu;
+    K4[g] = s_K4[g];
+  }
+  for (int32_t j = tid; j < n; j += TEAM) {
+    uint32_t b4[NG];
+    coded_load<NG>(C8, s_coloff, (int64_t)rr[j], b4);
+    if (s_park) {
+      if (NG >= 4) {
+#pragma unroll
+        for (int g = 0; g < NG; g += 4)
+          *reinterpret_cast<uint4 *>(s_park + (size_t)j * NG + g) = make_uint4(b4[g], b4[g + 1], b4[g + 2], b4[g + 3]);
+      } else {
+        *reinterpret_cast<uint2 *>(s_park + (size_t)j * NG) = make_uint2(b4[0], b4[1]);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+      mxB[g] = __vmaxu4(mxB[g], b4[g]);
+      mnB[g] = __vminu4(mnB[g], b4[g]);
+      mnT[g] = __vminu4(mnT[g], __vsub4(b4[g], K4[g]));  // NaN (byte 0 of a column with NaNs) -> 255
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < NG; g++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mxB[g] = __vmaxu4(mxB[g], __shfl_xor_sync(0xffffffffu, mxB[g], o));
+      mnB[g] = __vminu4(mnB[g], __shfl_xor_sync(0xffffffffu, mnB[g], o));
+      mnT[g] = __vminu4(mnT[g], __shfl_xor_sync(0xffffffffu, mnT[g], o));
+    }
+    if (lane == 0) {
+      s_cred[wit * 24 + g] = mnT[g];
+      s_cred[wit * 24 + 8 + g] = mxB[g];
+      s_cred[wit * 24 + 16 + g] = mnB[g];
+    }
+  }
+}
+
+// pass 2: side histograms.  Per 32 consecutive samples: one ballot per candidate, counted against the
+// class masks with lane == class.  sweep 0 counts x < cut, sweep 1 the NaN samples (pkg:244-248).
+template <int NG, int TEAM, typename LabFn>
+__device__ __forceinline__ void coded_pass2(const uint8_t *__restrict__ C8, const int64_t *s_coloff,
+                                            const uint32_t *s_K4, const uint32_t *s_t4, const uint32_t *s_e4, int sweep,
+                                            const int32_t *rr, LabFn lab, int32_t n, int C, int wit, int lane,
+                                            int32_t *s_hist, int hs, int hoff, int nb, const uint32_t *s_park) {
+  int32_t acc[4 * NG];
+  uint32_t K4[NG], t4[NG], e4[NG];
+#pragma unroll
+  for (int c = 0; c < 4 * NG; c++) acc[c] = 0;
+#pragma unroll
+  for (int g = 0; g < NG; g++) {
+    K4[g] = s_K4[g];
+    t4[g] = s_t4[g];
+    e4[g] = s_e4[g];
+  }
+  for (int32_t j0 = wit * 32; j0 < n; j0 += TEAM) {
+    const int32_t j = j0 + lane;
+    const bool valid = j < n;
+    const int32_t cls = valid ? lab(j) : -1;
+    uint32_t b4[NG];
+    if (s_park) {
+      const int32_t jp = valid ? j : 0;
+      if (NG >= 4) {
+#pragma unroll
+        for (int g = 0; g < NG; g += 4) {
+          const uint4 v = *reinterpret_cast<const uint4 *>(s_park + (size_t)jp * NG + g);
+          b4[g] = v.x;
+          b4[g + 1] = v.y;
+          b4[g + 2] = v.z;
+          b4[g + 3] = v.w;
+        }
+      } else {
+        const uint2 v = *reinterpret_cast<const uint2 *>(s_park + (size_t)jp * NG);
+        b4[0] = v.x;
+        b4[1] = v.y;
+      }
+    } else {
+      coded_load<NG>(C8, s_coloff, valid ? (int64_t)rr[j] : 0, b4);
+    }
+    uint32_t cmk = 0u;  // samples of this chunk whose class is this lane's index
+    for (int q2 = 0; q2 < C; q2++) {
+      const uint32_t m = __ballot_sync(0xffffffffu, cls == q2);
+      if (lane == q2) cmk = m;
+    }
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+      uint32_t l4 = sweep ? __vcmpeq4(b4[g], 0u) : __vcmpleu4(__vsub4(b4[g], K4[g]), t4[g]);
+      l4 &= e4[g];
+      if (!valid) l4 = 0u;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; q4++) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, (l4 >> (8 * q4)) & 1u);
+        acc[4 * g + q4] += __popc(bal & cmk);
+      }
+    }
+  }
+  if (lane < C) {
+#pragma unroll
+    for (int c = 0; c < 4 * NG; c++)
+      if (c < nb && acc[c]) atomicAdd(&s_hist[c * hs + hoff + lane], acc[c]);
+  }
+}
+
 template <int TASK, int TEAM, bool CODED>
 __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
                                   TEAM == 32 ? 5 : (TEAM == MID_TEAM ? (CODED ? 4 : 6) : 2))
@@ -457,6 +587,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
   uint32_t *s_cred = reinterpret_cast<uint32_t *>(smi + L.o_cred);
   uint8_t *s_thrb = reinterpret_cast<uint8_t *>(smi + L.o_cb), *s_enb = s_thrb + 32, *s_Kb = s_thrb + 64, *s_nanb = s_thrb + 96;
   int32_t *s_thr = smi + L.o_thr;
+  uint32_t *s_park = nullptr;  // see make_lay: o_park
 
   const int i = p.q_cur[qi][q];
   const int32_t tree = p.cur.tree[i], b = p.cur.begin[i], e = p.cur.end[i], n = e - b;
@@ -707,45 +838,13 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
         __syncthreads();
         const int ng = (nb + 3) >> 2;
         const uint32_t *s_K4 = reinterpret_cast<const uint32_t *>(s_Kb);
-        {
-          uint32_t mnT[8], mxB[8], mnB[8];
-#pragma unroll
-          for (int g = 0; g < 8; g++) {
-            mnT[g] = 0xffffffffu;
-            mxB[g] = 0u;
-            mnB[g] = 0xffffffffu;
-          }
-          for (int32_t j = tid; j < n; j += TEAM) {
-            const int64_t r = rr[j];
-#pragma unroll
-            for (int g = 0; g < 8; g++) {
-              if (g < ng) {
-                const uint32_t b0 = __ldg(p.C8 + s_coloff[4 * g + 0] + r), b1 = __ldg(p.C8 + s_coloff[4 * g + 1] + r);
-                const uint32_t b2 = __ldg(p.C8 + s_coloff[4 * g + 2] + r), b3 = __ldg(p.C8 + s_coloff[4 * g + 3] + r);
-                const uint32_t b4 = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
-                mxB[g] = __vmaxu4(mxB[g], b4);
-                mnB[g] = __vminu4(mnB[g], b4);
-                mnT[g] = __vminu4(mnT[g], __vsub4(b4, s_K4[g]));  // NaN (byte 0 of a column with NaNs) -> 255
-              }
-            }
-          }
-#pragma unroll
-          for (int g = 0; g < 8; g++) {
-            if (g < ng) {
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-                mxB[g] = __vmaxu4(mxB[g], __shfl_xor_sync(0xffffffffu, mxB[g], o));
-                mnB[g] = __vminu4(mnB[g], __shfl_xor_sync(0xffffffffu, mnB[g], o));
-                mnT[g] = __vminu4(mnT[g], __shfl_xor_sync(0xffffffffu, mnT[g], o));
-              }
-              if (lane == 0) {
-                s_cred[wit * 24 + g] = mnT[g];
-                s_cred[wit * 24 + 8 + g] = mxB[g];
-                s_cred[wit * 24 + 16 + g] = mnB[g];
-              }
-            }
-          }
-        }
+        // (slots of the last group past nb read column 0: harmless, never consumed)
+        if (ng <= 2)
+          coded_pass1<2, TEAM>(p.C8, s_coloff, s_K4, rr, n, tid, s_cred, wit, lane, s_park);
+        else if (ng <= 4)
+          coded_pass1<4, TEAM>(p.C8, s_coloff, s_K4, rr, n, tid, s_cred, wit, lane, s_park);
+        else
+          coded_pass1<8, TEAM>(p.C8, s_coloff, s_K4, rr, n, tid, s_cred, wit, lane, s_park);
         __syncthreads();
         // ---- per candidate: decode min / max, constant test, cutpoint, code threshold
         if (wit == 0) {
@@ -802,47 +901,22 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
           if (lane == 0) s_misc[3] = any_nan ? 1 : 0;
         }
         __syncthreads();
-        // ---- pass 2: side histograms.  Per 32 consecutive samples: one ballot per candidate, counted
-        //      against the class masks with lane == class.
-        const int nsweep = s_misc[3] ? 2 : 1;  // second sweep: NaN rows per class (pkg:244-248)
+        // ---- pass 2: side histograms (second sweep only if a candidate's column holds NaNs in this node)
+        const int nsweep = s_misc[3] ? 2 : 1;
+        auto lab = [&](int32_t j) -> int32_t { return LAB(j); };
         for (int sweep = 0; sweep < nsweep; sweep++) {
-          int32_t acc[32];
-#pragma unroll
-          for (int c = 0; c < 32; c++) acc[c] = 0;
           const uint32_t *s_t4 = reinterpret_cast<const uint32_t *>(s_thrb);
           const uint32_t *s_e4 = reinterpret_cast<const uint32_t *>(sweep ? s_nanb : s_enb);
-          for (int32_t j0 = wit * 32; j0 < n; j0 += TEAM) {
-            const int32_t j = j0 + lane;
-            const bool valid = j < n;
-            const int64_t r = valid ? rr[j] : 0;
-            const int32_t cls = valid ? LAB(j) : -1;
-            uint32_t cmk = 0u;  // samples of this chunk whose class is this lane's index
-            for (int q2 = 0; q2 < C; q2++) {
-              const uint32_t m = __ballot_sync(0xffffffffu, cls == q2);
-              if (lane == q2) cmk = m;
-            }
-#pragma unroll
-            for (int g = 0; g < 8; g++) {
-              if (g < ng) {
-                const uint32_t b0 = __ldg(p.C8 + s_coloff[4 * g + 0] + r), b1 = __ldg(p.C8 + s_coloff[4 * g + 1] + r);
-                const uint32_t b2 = __ldg(p.C8 + s_coloff[4 * g + 2] + r), b3 = __ldg(p.C8 + s_coloff[4 * g + 3] + r);
-                const uint32_t b4 = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
-                uint32_t l4 = sweep ? __vcmpeq4(b4, 0u) : __vcmpleu4(__vsub4(b4, s_K4[g]), s_t4[g]);
-                l4 &= s_e4[g];
-                if (!valid) l4 = 0u;
-#pragma unroll
-                for (int q4 = 0; q4 < 4; q4++) {
-                  const uint32_t bal = __ballot_sync(0xffffffffu, (l4 >> (8 * q4)) & 1u);
-                  acc[4 * g + q4] += __popc(bal & cmk);
-                }
-              }
-            }
-          }
-          if (lane < C) {
-#pragma unroll
-            for (int c = 0; c < 32; c++)
-              if (c < nb && acc[c]) atomicAdd(&s_hist[c * L.hs + (sweep ? C : 0) + lane], acc[c]);
-          }
+          const int hoff = sweep ? C : 0;
+          if (ng <= 2)
+            coded_pass2<2, TEAM>(p.C8, s_coloff, s_K4, s_t4, s_e4, sweep, rr, lab, n, C, wit, lane, s_hist, L.hs, hoff, nb,
+                                 s_park);
+          else if (ng <= 4)
+            coded_pass2<4, TEAM>(p.C8, s_coloff, s_K4, s_t4, s_e4, sweep, rr, lab, n, C, wit, lane, s_hist, L.hs, hoff, nb,
+                                 s_park);
+          else
+            coded_pass2<8, TEAM>(p.C8, s_coloff, s_K4, s_t4, s_e4, sweep, rr, lab, n, C, wit, lane, s_hist, L.hs, hoff, nb,
+                                 s_park);
         }
       } else {
       // ---- phase 1: the whole team on the samples of one candidate at a time
@@ -1400,8 +1474,10 @@ __device__ __noinline__ double var_reduction_bits(const uint32_t *s_lt, const ui
   return ET_DIV(ET_SUB(ET_SUB(V, a), bq), V);
 }
 
-template <int TASK, typename VT>
-__global__ void __launch_bounds__(32 * LANE_WARPS) k_lane(P p, int32_t qcount, int qi, int NW) {
+// SMALL: the classes of up to 64 samples run with a tighter register budget (more resident warps; these nodes
+// are dominated by fixed per-batch latency), the larger classes are shared-memory bound anyway.
+template <int TASK, typename VT, bool SMALL>
+__global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? 6 : 4) k_lane(P p, int32_t qcount, int qi, int NW) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool CODED = (sizeof(VT) != 8);
   constexpr uint32_t FULL = 0xffffffffu;
@@ -2051,8 +2127,11 @@ struct LevelCfg {
 
 template <int TASK, typename VT>
 void launch_lane(et_ctx *ctx, const P &p, int32_t count, int qi, int NW, size_t smem_per_warp, cudaStream_t st) {
-  k_lane<TASK, VT><<<(unsigned)ceil_div(count, LANE_WARPS), 32 * LANE_WARPS, smem_per_warp * LANE_WARPS, st>>>(
-      p, count, qi, NW);
+  const unsigned grid = (unsigned)ceil_div(count, LANE_WARPS);
+  if (NW <= 2)
+    k_lane<TASK, VT, true><<<grid, 32 * LANE_WARPS, smem_per_warp * LANE_WARPS, st>>>(p, count, qi, NW);
+  else
+    k_lane<TASK, VT, false><<<grid, 32 * LANE_WARPS, smem_per_warp * LANE_WARPS, st>>>(p, count, qi, NW);
   ctx->launches++;
 }
 
@@ -2147,10 +2226,12 @@ void set_smem_attr(const LevelCfg &lc) {
                                     (int)lc.smem_cta));
   }
   if (lc.coded) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(lc.smem_lane[1] * LANE_WARPS)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(lc.smem_lane[4] * LANE_WARPS)));
   } else {
-    CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(lc.smem_lane[0] * LANE_WARPS)));
     CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(lc.smem_warp * WARPS_PER_CTA)));
@@ -2458,10 +2539,11 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       sg.n_leaves = n_leaves;
       sg.nodes = nullptr;
       sg.leaves = nullptr;
-      if (cudaMalloc((void **)&sg.nodes, (size_t)n_nodes * sizeof(PNode)) != cudaSuccess ||
-          cudaMalloc((void **)&sg.leaves, std::max<size_t>(1, (size_t)n_leaves * lw) * sizeof(double)) != cudaSuccess) {
-        cudaGetLastError();
-        if (sg.nodes) cudaFree(sg.nodes);
+      sg.nodes = static_cast<PNode *>(et_dev_alloc(ctx, (size_t)n_nodes * sizeof(PNode)));
+      sg.leaves = static_cast<double *>(et_dev_alloc(ctx, std::max<size_t>(1, (size_t)n_leaves * lw) * sizeof(double)));
+      if (!sg.nodes || !sg.leaves) {
+        et_dev_free(ctx, sg.nodes, (size_t)n_nodes * sizeof(PNode));
+        et_dev_free(ctx, sg.leaves, std::max<size_t>(1, (size_t)n_leaves * lw) * sizeof(double));
         ET_FAIL(ET_ENOMEM, "cannot allocate the forest (%lld nodes)", (long long)n_nodes);
       }
       segs.push_back(sg);
@@ -2481,9 +2563,15 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
     // ---- the forest stays resident in HBM; batches are concatenated
     out->total_nodes = node_base;
     out->total_leaves = leaf_base;
+    auto free_seg = [&](Seg &sg) {
+      et_dev_free(ctx, sg.nodes, (size_t)sg.n_nodes * sizeof(PNode));
+      et_dev_free(ctx, sg.leaves, std::max<size_t>(1, (size_t)sg.n_leaves * lw) * sizeof(double));
+    };
     if (segs.size() == 1) {
       out->d_nodes = segs[0].nodes;
       out->d_leaf = segs[0].leaves;
+      out->nodes_bytes = (size_t)segs[0].n_nodes * sizeof(PNode);
+      out->leaf_bytes = std::max<size_t>(1, (size_t)segs[0].n_leaves * lw) * sizeof(double);
       segs.clear();
     } else {
       CUDA_CHECK(cudaMalloc((void **)&out->d_nodes, std::max<size_t>(1, (size_t)node_base) * sizeof(PNode)));
@@ -2498,10 +2586,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
         lo += sg.n_leaves;
       }
       CUDA_CHECK(cudaStreamSynchronize(st));
-      for (auto &sg : segs) {
-        cudaFree(sg.nodes);
-        cudaFree(sg.leaves);
-      }
+      for (auto &sg : segs) free_seg(sg);
       segs.clear();
     }
     CUDA_CHECK(cudaMalloc((void **)&out->d_tree_off, ((size_t)a.m + 1) * sizeof(int64_t)));
@@ -2519,8 +2604,8 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
   } catch (...) {
     cudaStreamSynchronize(st);
     for (auto &sg : segs) {
-      cudaFree(sg.nodes);
-      cudaFree(sg.leaves);
+      et_dev_free(ctx, sg.nodes, (size_t)sg.n_nodes * sizeof(PNode));
+      et_dev_free(ctx, sg.leaves, std::max<size_t>(1, (size_t)sg.n_leaves * lw) * sizeof(double));
     }
     free_tmp();
     throw;

@@ -154,6 +154,15 @@ __global__ void __launch_bounds__(256) k_col_encode(const double *__restrict__ X
 
 }  // namespace
 
+void et_data_drop_codes(et_data *D) {
+  et_dev_free(D->ctx, D->c8, (size_t)D->d * (size_t)D->ldc);
+  et_dev_free(D->ctx, D->dict, (size_t)D->d * 256 * sizeof(double));
+  et_dev_free(D->ctx, D->coff, (size_t)D->d);
+  D->c8 = nullptr;
+  D->dict = nullptr;
+  D->coff = nullptr;
+}
+
 // Builds (or refreshes) the coded copy of the table.  D->coded: 1 = codes valid, -1 = some column has
 // more than 256 distinct values (the builder then gathers FP64 values).
 void et_data_encode(et_ctx *ctx, et_data *D) {
@@ -167,23 +176,17 @@ void et_data_encode(et_ctx *ctx, et_data *D) {
   const int64_t n = D->n;
   const int32_t d = D->d;
   D->ldc = ((n + 127) / 128) * 128;
-  int32_t *d_cnt = nullptr;
+  int32_t *d_cnt = static_cast<int32_t *>(et_dev_alloc(ctx, (size_t)d * sizeof(int32_t)));
+  D->dict = static_cast<double *>(et_dev_alloc(ctx, (size_t)d * 256 * sizeof(double)));
+  D->coff = static_cast<uint8_t *>(et_dev_alloc(ctx, (size_t)d));
+  D->c8 = static_cast<uint8_t *>(et_dev_alloc(ctx, (size_t)d * (size_t)D->ldc));
   auto fail = [&](int code, const char *msg) {
-    if (d_cnt) cudaFree(d_cnt);
-    if (D->dict) cudaFree(D->dict);
-    if (D->c8) cudaFree(D->c8);
-    if (D->coff) cudaFree(D->coff);
-    D->dict = nullptr;
-    D->c8 = nullptr;
-    D->coff = nullptr;
+    et_dev_free(ctx, d_cnt, (size_t)d * sizeof(int32_t));
+    et_data_drop_codes(D);
     cudaGetLastError();
     ET_FAIL(code, "%s", msg);
   };
-  if (cudaMalloc((void **)&d_cnt, (size_t)d * sizeof(int32_t)) != cudaSuccess ||
-      cudaMalloc((void **)&D->dict, (size_t)d * 256 * sizeof(double)) != cudaSuccess ||
-      cudaMalloc((void **)&D->coff, (size_t)d) != cudaSuccess ||
-      cudaMalloc((void **)&D->c8, (size_t)d * (size_t)D->ldc) != cudaSuccess)
-    fail(ET_ENOMEM, "cannot allocate the coded copy of the table");
+  if (!d_cnt || !D->dict || !D->coff || !D->c8) fail(ET_ENOMEM, "cannot allocate the coded copy of the table");
   k_col_dict<<<(unsigned)d, 256, 0, st>>>(D->x, D->ld, n, D->dict, d_cnt, D->coff);
   dim3 grid((unsigned)ceil_div(D->ldc, 1024), (unsigned)d);
   k_col_encode<<<grid, 256, 0, st>>>(D->x, D->ld, n, D->dict, d_cnt, D->coff, D->c8, D->ldc);
@@ -192,17 +195,12 @@ void et_data_encode(et_ctx *ctx, et_data *D) {
   if (cudaMemcpyAsync(h_cnt.data(), d_cnt, (size_t)d * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
       cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)
     fail(ET_ECUDA, "coding the table failed");
-  cudaFree(d_cnt);
+  et_dev_free(ctx, d_cnt, (size_t)d * sizeof(int32_t));
   d_cnt = nullptr;
   bool ok = true;
   for (int32_t f = 0; f < d; f++) ok &= (h_cnt[(size_t)f] <= 256);
   if (!ok) {
-    cudaFree(D->dict);
-    cudaFree(D->c8);
-    cudaFree(D->coff);
-    D->dict = nullptr;
-    D->c8 = nullptr;
-    D->coff = nullptr;
+    et_data_drop_codes(D);
     D->coded = -1;
     return;
   }

@@ -9,14 +9,25 @@ struct et_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;  // the one work is queued on (own or caller's)
   int sm_count = 148;
-  std::mutex mu;  // a context serialises its calls
+  std::recursive_mutex mu;  // a context serialises its calls (recursive: handles are freed inside locked calls)
   int64_t launches = 0;
   Workspace *ws = nullptr;
   // side streams: the node kernels of one level (one launch per size class) run concurrently
+  // freed device blocks of tables / forests kept for the next call of the same shape (exact-size reuse), so a
+  // build-after-build loop does no cudaMalloc / cudaFree in the steady state
+  struct Block {
+    void *p;
+    size_t bytes;
+  };
+  std::vector<Block> cache;
+  size_t cache_bytes = 0;
   cudaStream_t side[7] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[7] = {};
 };
 void et_workspace_free(Workspace *ws);
+// api.cu: device blocks through the context's cache (null on failure, like cudaMalloc != cudaSuccess)
+void *et_dev_alloc(et_ctx *ctx, size_t bytes);
+void et_dev_free(et_ctx *ctx, void *p, size_t bytes);
 
 struct et_data {
   et_ctx *ctx = nullptr;
@@ -24,6 +35,7 @@ struct et_data {
   int32_t d = 0;
   int64_t ld = 0;       // column stride in elements (n rounded up to 16)
   double *x = nullptr;  // column-major [d][ld], resident in HBM
+  size_t x_bytes = 0;
   // order-preserving byte codes of the same table (encode.cu): byte + coff[col] = 0 for NaN, r + 1 for dict[col][r]
   int coded = 0;           // 0 not prepared yet, 1 codes valid, -1 not codable (> 256 distinct values in a column)
   uint8_t *c8 = nullptr;   // column-major [d][ldc]
@@ -61,6 +73,7 @@ struct et_forest {
   int64_t *d_tree_off = nullptr;  // m + 1
   PNode *d_nodes = nullptr;       // total_nodes
   double *d_leaf = nullptr;       // total_leaves x leaf_width
+  size_t nodes_bytes = 0, leaf_bytes = 0;  // allocation sizes when the blocks came from et_dev_alloc (else 0)
   // lazily fetched host copy (export)
   bool host_ready = false;
   std::vector<PNode> h_nodes;
@@ -79,6 +92,7 @@ struct BuildArgs {
 
 // encode.cu
 void et_data_encode(et_ctx *ctx, et_data *data);
+void et_data_drop_codes(et_data *data);  // gives the coded copy back to the context's block cache
 // build.cu
 void et_build_forest(et_ctx *ctx, et_data *data, const BuildArgs &a, et_forest *out, et_stats *stats);
 // predict.cu

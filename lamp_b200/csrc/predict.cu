@@ -10,69 +10,96 @@
 
 #include "internal.h"
 
-// One thread per row; the row's features are read straight from the row-major matrix (the rows of
-// a block are contiguous, so the lines it touches are shared in L1/L2).  Per-class sums are kept in
-// shared memory in [class][thread] order and accumulated in tree order, like the reference's
-// sequential mean over trees (pkg:549,584).
-template <bool REG>
-__global__ void __launch_bounds__(128) k_predict(const PNode *__restrict__ nodes, const int64_t *__restrict__ tree_off,
+// A CTA owns R rows; its 256 threads are R x TS (row, tree-slice) pairs.  Traversal is parallel over
+// (row, tree): thread (r, s) walks trees s, s + TS, ... of the current block of trees for row r and
+// parks the leaf it reaches in shared memory.  The per-class sums are then accumulated by one thread
+// per (row, class) IN TREE ORDER, like the reference's sequential mean over trees (pkg:549,584), so the
+// result is bit-identical to the one-thread-per-row walk while 256/R times more walks are in flight.
+// Threads of one slice walk the same tree for neighbouring rows, so a tree's top levels stay in L1.
+// STAGE: the CTA's rows are staged once in shared memory (coalesced), so every feature lookup of the walks
+// is a shared-memory read instead of a scattered 8-byte read of a row-major matrix larger than L2.
+template <bool STAGE>
+__global__ void __launch_bounds__(256) k_predict(const PNode *__restrict__ nodes, const int64_t *__restrict__ tree_off,
                                                  const double *__restrict__ leaves, int32_t m, int32_t lw,
                                                  const double *__restrict__ x, int64_t n, int32_t d,
-                                                 double *__restrict__ out, int sum_only) {
-  extern __shared__ double acc[];  // [lw][blockDim.x]
-  int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= n) return;
-  const double *xr = x + row * (int64_t)d;
-  double racc = 0.0;
-  if (!REG)
-    for (int c = 0; c < lw; c++) acc[c * blockDim.x + threadIdx.x] = 0.0;
-  for (int32_t t = 0; t < m; t++) {
-    const PNode *tn = nodes + tree_off[t];
-    int32_t id = 0;
-    PNode p = tn[0];
-    while (p.feat >= 0) {
-      double v = xr[p.feat & (ET_MIL_BIT - 1)];
-      bool left = (v < p.cut) || ((p.feat & ET_MIL_BIT) && (v != v));
-      id = left ? id + 1 : p.right_or_leaf;
-      p = tn[id];
-    }
-    const double *lv = leaves + (int64_t)p.right_or_leaf * lw;
-    if (REG) {
-      racc = ET_ADD(racc, lv[0]);
-    } else {
-      for (int c = 0; c < lw; c++) {
-        double *a = &acc[c * blockDim.x + threadIdx.x];
-        *a = ET_ADD(*a, lv[c]);
+                                                 double *__restrict__ out, int sum_only, int R, int TB) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *s_acc = reinterpret_cast<double *>(smem_raw);              // [R][lw]
+  double *s_x = s_acc + R * lw;                                      // [R][d] (STAGE)
+  int32_t *s_leaf = reinterpret_cast<int32_t *>(s_x + (STAGE ? (size_t)R * d : 0));  // [R][TB]
+  const int TS = 256 / R;
+  const int r = threadIdx.x / TS, sl = threadIdx.x % TS;
+  const int64_t row0 = (int64_t)blockIdx.x * R;
+  const int64_t row = row0 + r;
+  const bool has_row = row < n;
+  const double *xr = STAGE ? (s_x + (size_t)r * d) : (x + (has_row ? row : 0) * (int64_t)d);
+  for (int q = threadIdx.x; q < R * lw; q += 256) s_acc[q] = 0.0;
+  if (STAGE) {
+    const int64_t rows_here = min((int64_t)R, n - row0);
+    const double *src = x + row0 * (int64_t)d;  // the CTA's rows are contiguous in the row-major matrix
+    for (int64_t q = threadIdx.x; q < rows_here * d; q += 256) s_x[q] = src[q];
+    __syncthreads();
+  }
+  for (int32_t t0 = 0; t0 < m; t0 += TB) {
+    const int32_t tb = min(TB, m - t0);
+    if (has_row) {
+      for (int32_t t = sl; t < tb; t += TS) {
+        const PNode *tn = nodes + tree_off[t0 + t];
+        int32_t id = 0;
+        PNode pn = tn[0];
+        while (pn.feat >= 0) {
+          const double v = xr[pn.feat & (ET_MIL_BIT - 1)];
+          const bool left = (v < pn.cut) || ((pn.feat & ET_MIL_BIT) && (v != v));
+          id = left ? id + 1 : pn.right_or_leaf;
+          pn = tn[id];
+        }
+        s_leaf[r * TB + t] = pn.right_or_leaf;
       }
     }
+    __syncthreads();
+    for (int q = threadIdx.x; q < R * lw; q += 256) {
+      const int rr = q / lw, c = q - rr * lw;
+      if (row0 + rr < n) {
+        double a = s_acc[q];
+        const int32_t *lf = s_leaf + rr * TB;
+        for (int32_t t = 0; t < tb; t++) a = ET_ADD(a, leaves[(int64_t)lf[t] * lw + c]);
+        s_acc[q] = a;
+      }
+    }
+    __syncthreads();
   }
-  double dm = (double)m;
-  if (REG) {
-    out[row] = sum_only ? racc : ET_DIV(racc, dm);
-  } else {
-    for (int c = 0; c < lw; c++) {
-      double a = acc[c * blockDim.x + threadIdx.x];
-      out[row * lw + c] = sum_only ? a : ET_DIV(a, dm);
+  const double dm = (double)m;
+  for (int q = threadIdx.x; q < R * lw; q += 256) {
+    const int rr = q / lw, c = q - rr * lw;
+    if (row0 + rr < n) {
+      const double a = s_acc[q];
+      out[(row0 + rr) * lw + c] = sum_only ? a : ET_DIV(a, dm);
     }
   }
 }
 
 void et_predict_device_impl(et_ctx *ctx, et_forest *f, const double *x, int64_t n, int32_t d, double *out,
                             int sum_only) {
-  int32_t m = f->m;
-  int lw = f->leaf_width;
-  const int threads = 128;
-  size_t smem = f->is_regression ? 0 : (size_t)lw * threads * sizeof(double);
+  const int32_t m = f->m;
+  const int lw = f->leaf_width;
+  const int TB = std::max(1, std::min(m, 1024));
+  // rows per CTA: as many as keep the CTA's shared memory near 48 KB (4+ CTAs per SM); the rows themselves are
+  // staged when one row fits in 24 KB
+  const bool stage = (size_t)d * 8 <= 24 * 1024;
+  const size_t per_row = (size_t)TB * 4 + (size_t)lw * 8 + (stage ? (size_t)d * 8 : 0);
+  int R = 16;
+  while (R > 1 && (size_t)R * per_row > 48 * 1024) R /= 2;
+  const size_t smem = (size_t)R * per_row;
   if (smem > 200 * 1024) ET_FAIL(ET_EUNSUPPORTED, "predict: numClasses=%d needs more shared memory than one SM has", lw);
-  unsigned grid = (unsigned)ceil_div(n, threads);
-  const PNode *nodes = f->d_nodes;
-  if (f->is_regression) {
-    k_predict<true><<<grid, threads, 0, ctx->stream>>>(nodes, f->d_tree_off, f->d_leaf, m, lw, x, n, d, out, sum_only);
+  const unsigned grid = (unsigned)ceil_div(n, R);
+  if (stage) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_predict<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_predict<true><<<grid, 256, smem, ctx->stream>>>(f->d_nodes, f->d_tree_off, f->d_leaf, m, lw, x, n, d, out, sum_only,
+                                                      R, TB);
   } else {
-    if (smem > 48 * 1024)
-      CUDA_CHECK(cudaFuncSetAttribute(k_predict<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_predict<false><<<grid, threads, smem, ctx->stream>>>(nodes, f->d_tree_off, f->d_leaf, m, lw, x, n, d, out,
-                                                           sum_only);
+    CUDA_CHECK(cudaFuncSetAttribute(k_predict<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_predict<false><<<grid, 256, smem, ctx->stream>>>(f->d_nodes, f->d_tree_off, f->d_leaf, m, lw, x, n, d, out,
+                                                       sum_only, R, TB);
   }
   ctx->launches++;
   CUDA_CHECK(cudaGetLastError());

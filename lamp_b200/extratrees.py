@@ -286,6 +286,41 @@ class Forest(Sequence):
         out["regression"] = self.regression
         return out
 
+    PACKED_NODE = np.dtype([("cut", np.float64), ("feat", np.int32), ("right_or_leaf", np.int32)])
+
+    def export_packed(self, nodes_out=None, leaves_out=None) -> dict:
+        """The forest in the device layout (et_forest_export_packed): 16-byte pre-order node records, the
+        compact leaf table and the tree offsets, copied device->host as they are.  `nodes_out` / `leaves_out`
+        may be preallocated (e.g. pinned) buffers at least as large as needed."""
+        tn, tl = C.c_int64(), C.c_int64()
+        check(capi.lib().et_forest_packed_dims(self.h, C.byref(tn), C.byref(tl)))
+        tn, tl = tn.value, tl.value
+        nodes = np.empty(tn, self.PACKED_NODE) if nodes_out is None else nodes_out[:tn]
+        leaves = np.empty((tl, self.leaf_width), np.float64) if leaves_out is None else \
+            leaves_out.reshape(-1)[:tl * self.leaf_width].reshape(tl, self.leaf_width)
+        if nodes.dtype != self.PACKED_NODE or len(nodes) != tn or not nodes.flags.c_contiguous:
+            raise ValueError("nodes_out must be a contiguous PACKED_NODE array with room for the forest")
+        if leaves.dtype != np.float64 or leaves.size != tl * self.leaf_width or not leaves.flags.c_contiguous:
+            raise ValueError("leaves_out must be a contiguous float64 array with room for the leaf table")
+        off = np.empty(self.m + 1, np.int64)
+        check(capi.lib().et_forest_export_packed(self.h, C.c_void_p(nodes.ctypes.data), C.c_void_p(leaves.ctypes.data),
+                                                 C.c_void_p(off.ctypes.data)))
+        return dict(nodes=nodes, leaves=leaves, tree_off=off, leaf_width=self.leaf_width, regression=self.regression)
+
+    @staticmethod
+    def import_packed(ser: dict, ctx: Optional[Context] = None) -> "Forest":
+        ctx = ctx or default_context()
+        nodes = np.ascontiguousarray(ser["nodes"], dtype=Forest.PACKED_NODE)
+        leaves = np.ascontiguousarray(ser["leaves"], dtype=np.float64)
+        off = np.ascontiguousarray(ser["tree_off"], dtype=np.int64)
+        lw = int(ser["leaf_width"])
+        h = C.c_void_p()
+        check(capi.lib().et_forest_import_packed(ctx.h, len(off) - 1, lw, int(ser["regression"]), len(nodes),
+                                                 leaves.size // lw, C.c_void_p(nodes.ctypes.data),
+                                                 C.c_void_p(leaves.ctypes.data), C.c_void_p(off.ctypes.data),
+                                                 C.byref(h)))
+        return Forest(ctx, h)
+
     @staticmethod
     def import_arrays(ser: dict, ctx: Optional[Context] = None) -> "Forest":
         ctx = ctx or default_context()

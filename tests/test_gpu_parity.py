@@ -209,3 +209,29 @@ def test_require_failures():
         et.buildForestClassification(x, np.zeros(4, np.int32), [1.0, -1.0, 1.0, 1.0], 2, 2, 1, 1, 1)
     with pytest.raises(ValueError):  # pkg:715-718
         et.buildForestRegression(x, np.zeros(5), 2, 1, 1, 1)
+
+
+def test_packed_export_import_roundtrip(mnist):
+    """The packed (device-layout) serialization: export -> import gives the same predictions, and the node
+    records agree with the per-tree export."""
+    x, y = mnist
+    x, y = x[:2000], y[:2000]
+    f = et.buildForestClassification(x, y, None, 10, 2, 28, 6, 4, seed=3)
+    ser = f.export_packed()
+    assert ser["tree_off"][0] == 0 and ser["tree_off"][-1] == len(ser["nodes"]) == f.total_nodes
+    g = et.Forest.import_packed(ser)
+    assert np.array_equal(et.predictClassification(f, x), et.predictClassification(g, x))
+    for t in (0, 5):
+        ft = f.flat(t)
+        a, b = ser["tree_off"][t], ser["tree_off"][t + 1]
+        nodes = ser["nodes"][a:b]
+        split = nodes["feat"] >= 0
+        assert np.array_equal(np.where(split, nodes["feat"] & 0x3FFFFFFF, -1), ft.feature)
+        assert np.array_equal(nodes["cut"][split].view(np.int64), ft.cut[split].view(np.int64))
+        assert np.array_equal(nodes["right_or_leaf"][split], ft.right[split])
+        assert np.array_equal(ser["leaves"][nodes["right_or_leaf"][~split]], ft.leaf[~split])
+    with pytest.raises(ValueError):  # ET_EINVAL surfaces like the reference's IllegalArgumentException
+        bad = dict(ser)
+        bad["tree_off"] = ser["tree_off"].copy()
+        bad["tree_off"][-1] += 1
+        et.Forest.import_packed(bad)
