@@ -111,6 +111,12 @@ typedef struct et_stats {
   double gpu_ms;       /* device time of the call (CUDA events on the context's stream)    */
   double gpu_ms_split; /* ... of which split-search kernels (min/max + score)              */
   double gpu_ms_partition;
+  /* Regression nodes of more than 2048 samples are scored from fixed-shape parallel sums instead of the
+   * reference's sequential order (deterministic, ~1e-15 of the node variance from the exactly rounded score):
+   * how many such nodes were searched, and in how many of them the best two candidates scored within 1e-9
+   * (relative) of each other -- the only places where the chosen split could differ from the reference's. */
+  int64_t parallel_sum_nodes;
+  int64_t ambiguous_splits;
 } et_stats;
 
 /* ---- build ---------------------------------------------------------------------------------

@@ -27,7 +27,8 @@ class EtReplay(C.Structure):
 class EtStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("v_mm", "v_sc", "s_rows", "p_rows", "draws", "const_hits", "scored",
                                          "nodes", "levels", "rounds", "launches", "replay_mismatches")] + \
-               [(n, C.c_double) for n in ("gpu_ms", "gpu_ms_split", "gpu_ms_partition")]
+               [(n, C.c_double) for n in ("gpu_ms", "gpu_ms_split", "gpu_ms_partition")] + \
+               [(n, C.c_int64) for n in ("parallel_sum_nodes", "ambiguous_splits")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -35,7 +35,7 @@ namespace {
 
 enum { TASK_CLS = 0, TASK_CLSW = 1, TASK_REG = 2 };
 enum { CF_CONST = 1, CF_NAN = 2, CF_MIL = 4 };
-enum { ST_VMM = 0, ST_VSC, ST_SROWS, ST_PROWS, ST_DRAWS, ST_CONST, ST_SCORED, ST_MISMATCH, ST_COUNT };
+enum { ST_VMM = 0, ST_VSC, ST_SROWS, ST_PROWS, ST_DRAWS, ST_CONST, ST_SCORED, ST_MISMATCH, ST_PARNODES, ST_AMBIG, ST_COUNT };
 
 constexpr int NT_MAX = 32;        // "tiny" nodes: one warp per node, one LANE per candidate
 constexpr int NW_MAX = 512;       // nodes up to this many samples are owned by one warp (lanes on samples)
@@ -287,6 +287,40 @@ __device__ __forceinline__ bool team_all(bool v, int32_t *redi) {
     r = a;
   }
   return r;
+}
+
+// fixed-shape sum over the team (butterfly inside a warp, then the warps in index order): the same
+// inputs always give the same bits, independent of scheduling; result valid in every thread
+template <int TEAM>
+__device__ __forceinline__ double team_sum(double v, double *redd) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = ET_ADD(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (TEAM > 32) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = TEAM / 32;
+    __syncthreads();
+    if (lane == 0) redd[w] = v;
+    __syncthreads();
+    double a = 0.0;
+    for (int q = 0; q < nw; q++) a = ET_ADD(a, redd[q]);
+    v = a;
+  }
+  return v;
+}
+
+// Variance-reduction score of a side (n_in, S_in, Q_in) = count, sum and sum of squares of (y - mu) over
+// the samples going left, mu = the node's mean (pkg:1196-1218 evaluated from moments about the node mean;
+// used for nodes too large for the reference's sequential order to be affordable, see k_node REGPAR).
+__device__ __forceinline__ double var_reduction_moments(int32_t n, double S_tot, double Q_tot, double V, int32_t ni,
+                                                        double Si, double Qi) {
+  const int32_t no = n - ni;
+  if (ni < 1 || no < 1) return NAN;
+  const double So = ET_SUB(S_tot, Si), Qo = ET_SUB(Q_tot, Qi);
+  const double dni = (double)ni, dno = (double)no, dn = (double)n;
+  const double vi = (ni == 1) ? 0.0 : ET_DIV(ET_SUB(Qi, ET_DIV(ET_MUL(Si, Si), dni)), dni);
+  const double vo = (no == 1) ? 0.0 : ET_DIV(ET_SUB(Qo, ET_DIV(ET_MUL(So, So), dno)), dno);
+  const double a = ET_MUL(ET_DIV(dni, dn), vi);
+  const double bq = ET_MUL(ET_DIV(dno, dn), vo);
+  return ET_DIV(ET_SUB(ET_SUB(V, a), bq), V);
 }
 
 // ---- exact scores ---------------------------------------------------------------------------
@@ -564,6 +598,14 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool WARP = (TEAM == 32);
   static_assert(!CODED || (TASK == TASK_CLS && TEAM > 32), "byte-coded teams: unweighted classification, CTA teams");
+  // Regression nodes of more than NM_MAX samples: the reference sums targets sequentially in subset order
+  // (saddle's two-pass sampleVariance), which one thread would have to replay for up to a million samples per
+  // candidate.  These nodes are scored from fixed-shape parallel sums of moments about the node mean instead:
+  // deterministic, within ~1e-15 (relative to the node variance) of the exactly rounded value -- closer to it
+  // than the reference's own sequential sum -- but not order-identical, so two candidates whose scores differ by
+  // less than that could swap.  Such splits are counted (et_stats.ambiguous_splits; 1e-9 relative) so that a
+  // replay run can tell.  Smaller nodes (where exact ties live) keep the exact sequential evaluation.
+  constexpr bool REGPAR = (TASK == TASK_REG && TEAM == CTA_TEAM && !CODED);
   const int tic = WARP ? (threadIdx.x >> 5) : 0;
   const int q = WARP ? blockIdx.x * WARPS_PER_CTA + tic : blockIdx.x;
   if (q >= qcount) return;
@@ -628,6 +670,8 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
   // ---------------- stop rules + node totals ----------------
   bool leaf;
   double total = 0.0, nsum = (double)n, leaf_mean = 0.0;
+  double reg_mu = 0.0, reg_S = 0.0, reg_Q = 0.0;  // REGPAR: node mean, sum and sum of squares of (y - mean)
+  double second_score = -INFINITY;                // REGPAR: runner-up score (ambiguity check)
   if (TASK == TASK_CLS) {
     for (int c = tid; c < C; c += TEAM) s_hnode[c] = p.cur.hist[(int64_t)i * C + c];
     team_sync<TEAM>();
@@ -649,6 +693,23 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
     for (int32_t j = tid; j < n; j += TEAM) uni &= !(yy[j] != head);
     uni = team_all<TEAM>(uni, s_redi);
     leaf = (n < p.n_min) || (depth >= p.max_depth) || uni;  // pkg:813-814
+    if (REGPAR) {
+      double s1 = 0.0;
+      for (int32_t j = tid; j < n; j += TEAM) s1 = ET_ADD(s1, yy[j]);
+      const double dn = (double)n;
+      reg_mu = ET_DIV(team_sum<TEAM>(s1, s_redd), dn);
+      double q1 = 0.0, s2 = 0.0;
+      for (int32_t j = tid; j < n; j += TEAM) {
+        const double dl = ET_SUB(yy[j], reg_mu);
+        s2 = ET_ADD(s2, dl);
+        q1 = ET_ADD(q1, ET_MUL(dl, dl));
+      }
+      reg_S = team_sum<TEAM>(s2, s_redd);
+      reg_Q = team_sum<TEAM>(q1, s_redd);
+      leaf_mean = reg_mu;
+      total = ET_DIV(ET_SUB(reg_Q, ET_DIV(ET_MUL(reg_S, reg_S), dn)), dn);
+      __syncthreads();
+    } else {
     // mean2 (pkg:782) and varianceNoSplit (pkg:436-437), sequential in subset order
     if (tid == 0) {
       double sum = 0.0;
@@ -675,6 +736,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
     leaf_mean = s_score[0];
     total = s_score[NB];
     team_sync<TEAM>();
+    }
   } else {
     const int32_t head = ll[0];
     bool uni = true;
@@ -743,7 +805,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
     }
     uint32_t *g_bits = nullptr;  // CTA teams keep side bitmasks in global scratch
     const int words = nv;
-    if (TASK != TASK_CLS && !WARP) {
+    if (TASK != TASK_CLS && !WARP && !REGPAR) {
       if (tid == 0) {
         unsigned long long off =
             atomicAdd(&p.cnt->scratch_words, (unsigned long long)NB * 2ull * (unsigned long long)words);
@@ -825,7 +887,161 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
       if (TASK == TASK_CLS)
         for (int t = tid; t < nb * L.hs; t += TEAM) s_hist[t] = 0;
       team_sync<TEAM>();
-      if (CODED) {
+      if (REGPAR) {
+        // ---- large regression node: groups of 4 candidates; per group one pass for min / max and one for the
+        //      moments of the left side (a second sweep over the NaN samples only if a candidate has any)
+        double *scr = s_xs;  // reduction scratch [warp][12] (the value-staging buffer is unused here)
+        constexpr int NWP = TEAM / 32;
+        for (int g0 = 0; g0 < nb; g0 += 4) {
+          const double *colp[4];
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const int32_t f = (g0 + c < nb) ? s_feat[g0 + c] : -1;
+            colp[c] = p.X + (int64_t)(f >= 0 ? f : 0) * p.ld;
+          }
+          {
+            double mn[4], mx[4];
+            uint32_t nanm = 0u;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+              mn[c] = 1.7976931348623157e308;  // pkg:35-36
+              mx[c] = -1.7976931348623157e308;
+            }
+            for (int32_t j = tid; j < n; j += TEAM) {
+              const int32_t r = rr[j];
+              double x[4];
+#pragma unroll
+              for (int c = 0; c < 4; c++) x[c] = __ldg(colp[c] + r);
+#pragma unroll
+              for (int c = 0; c < 4; c++) {
+                if (x[c] < mn[c]) mn[c] = x[c];
+                if (x[c] > mx[c]) mx[c] = x[c];
+                nanm |= (uint32_t)(x[c] != x[c]) << c;
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                const double omn = __shfl_xor_sync(0xffffffffu, mn[c], o), omx = __shfl_xor_sync(0xffffffffu, mx[c], o);
+                if (omn < mn[c]) mn[c] = omn;
+                if (omx > mx[c]) mx[c] = omx;
+              }
+            }
+            nanm = __reduce_or_sync(0xffffffffu, nanm);
+            __syncthreads();  // previous users of the scratch are done
+            if (lane == 0) {
+#pragma unroll
+              for (int c = 0; c < 4; c++) {
+                scr[wit * 12 + c] = mn[c];
+                scr[wit * 12 + 4 + c] = mx[c];
+              }
+              s_redi[wit] = (int32_t)nanm;
+            }
+          }
+          __syncthreads();
+          if (tid < 4 && g0 + tid < nb && s_feat[g0 + tid] >= 0) {
+            const int c = tid, ci = g0 + tid;
+            double a = 1.7976931348623157e308, bq = -1.7976931348623157e308;
+            int has_nan = 0;
+            for (int w2 = 0; w2 < NWP; w2++) {
+              const double v1 = scr[w2 * 12 + c], v2 = scr[w2 * 12 + 4 + c];
+              if (v1 < a) a = v1;
+              if (v2 > bq) bq = v2;
+              has_nan |= (s_redi[w2] >> c) & 1;
+            }
+            if (bq <= a && !has_nan) {  // pkg:236
+              s_flags[ci] |= CF_CONST;
+            } else {
+              s_cut[ci] = ET_ADD(a, ET_MUL(ET_SUB(bq, a), s_u[ci]));  // nextDouble(min, max), pkg:240
+              if (has_nan) s_flags[ci] |= CF_NAN;
+            }
+          }
+          __syncthreads();
+          double cut[4];
+          int any_nan = 0;
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const int ci = min(g0 + c, nb - 1);
+            cut[c] = s_cut[ci];
+            any_nan |= (g0 + c < nb) && (s_flags[ci] & CF_NAN) && !(s_flags[ci] & CF_CONST);
+          }
+          int32_t keep_n = 0;  // thread c < 4: the x < cut side of candidate c
+          double keep_S = 0.0, keep_Q = 0.0, res_sn = NAN, res_sl = NAN;
+          int32_t nin_n = 0, nin_l = 0;
+          for (int sweep = 0; sweep < (any_nan ? 2 : 1); sweep++) {
+            int32_t cnt[4];
+            double S[4], Q[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+              cnt[c] = 0;
+              S[c] = 0.0;
+              Q[c] = 0.0;
+            }
+            for (int32_t j = tid; j < n; j += TEAM) {
+              const int32_t r = rr[j];
+              double x[4];
+#pragma unroll
+              for (int c = 0; c < 4; c++) x[c] = __ldg(colp[c] + r);
+              const double yd = ET_SUB(yy[j], reg_mu), yd2 = ET_MUL(yd, yd);
+#pragma unroll
+              for (int c = 0; c < 4; c++) {
+                const bool in = sweep ? (x[c] != x[c]) : (x[c] < cut[c]);
+                cnt[c] += in ? 1 : 0;
+                S[c] = ET_ADD(S[c], in ? yd : 0.0);
+                Q[c] = ET_ADD(Q[c], in ? yd2 : 0.0);
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                cnt[c] += __shfl_xor_sync(0xffffffffu, cnt[c], o);
+                S[c] = ET_ADD(S[c], __shfl_xor_sync(0xffffffffu, S[c], o));
+                Q[c] = ET_ADD(Q[c], __shfl_xor_sync(0xffffffffu, Q[c], o));
+              }
+            }
+            __syncthreads();
+            if (lane == 0) {
+#pragma unroll
+              for (int c = 0; c < 4; c++) {
+                scr[wit * 12 + c] = S[c];
+                scr[wit * 12 + 4 + c] = Q[c];
+                s_redi[wit * 4 + c] = cnt[c];
+              }
+            }
+            __syncthreads();
+            if (tid < 4) {
+              const int c = tid;
+              int32_t ni = 0;
+              double Si = 0.0, Qi = 0.0;
+              for (int w2 = 0; w2 < NWP; w2++) {
+                ni += s_redi[w2 * 4 + c];
+                Si = ET_ADD(Si, scr[w2 * 12 + c]);
+                Qi = ET_ADD(Qi, scr[w2 * 12 + 4 + c]);
+              }
+              if (sweep == 0) {
+                keep_n = ni;
+                keep_S = Si;
+                keep_Q = Qi;
+                nin_n = ni;
+                res_sn = var_reduction_moments(n, reg_S, reg_Q, total, ni, Si, Qi);
+              } else {
+                nin_l = keep_n + ni;
+                res_sl = var_reduction_moments(n, reg_S, reg_Q, total, nin_l, ET_ADD(keep_S, Si), ET_ADD(keep_Q, Qi));
+              }
+            }
+          }
+          if (tid < 4 && g0 + tid < nb && s_feat[g0 + tid] >= 0 && !(s_flags[g0 + tid] & CF_CONST)) {
+            const int ci = g0 + tid;
+            const double sn = res_sn, sl = (s_flags[ci] & CF_NAN) ? res_sl : NAN;
+            const bool mil = !(sl != sl) && (sl > sn || (sn != sn));  // pkg:272-275
+            s_score[ci] = mil ? sl : sn;
+            s_nleft[ci] = mil ? nin_l : nin_n;
+            if (mil) s_flags[ci] |= CF_MIL;
+          }
+        }
+      } else if (CODED) {
         // ---- phase 1 (byte-coded table): the team streams the node's samples ONCE per pass for the whole
         //      batch.  A thread owns a sample and reads its byte in every candidate's column (a warp reads
         //      32 nearby bytes per column); per-candidate min / max live in packed bytes (4 candidates per
@@ -1102,7 +1318,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
       }
       team_sync<TEAM>();
       // ---- phase 2: one thread per candidate evaluates the reference's score expression exactly
-      if (tid < nb && s_feat[tid] >= 0 && !(s_flags[tid] & CF_CONST)) {
+      if (!REGPAR && tid < nb && s_feat[tid] >= 0 && !(s_flags[tid] & CF_CONST)) {
         const int c = tid;
         const bool has_nan = (s_flags[c] & CF_NAN) != 0;
         double sn, sl = NAN;
@@ -1166,6 +1382,18 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
             bl = ol;
           }
         }
+        if (REGPAR) {
+          // runner-up over everything seen so far (for the ambiguity count)
+          double b2 = (counted && lane != bl) ? s : -INFINITY;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) b2 = fmax(b2, __shfl_xor_sync(0xffffffffu, b2, o));
+          if (bl < 32) {
+            if (bs > best_score)
+              second_score = fmax(best_score, fmax(second_score, b2));
+            else
+              second_score = fmax(second_score, bs);
+          }
+        }
         if (bl < 32 && bs > best_score) {
           best_score = bs;
           best_feature = s_feat[bl];
@@ -1211,6 +1439,13 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
       if (trace_split == make_leaf) st_mismatch++;
       if (st_mismatch) atomicAdd(&p.cnt->st[ST_MISMATCH], st_mismatch);
     }
+    if (REGPAR && !leaf) {
+      atomicAdd(&p.cnt->st[ST_PARNODES], 1ull);
+      if (best_feature >= 0 && second_score > -INFINITY &&
+          best_score > second_score &&  // (an exact tie comes from identical partitions: first wins, like the reference)
+          ET_SUB(best_score, second_score) <= 1e-9 * fmax(fabs(best_score), 1e-300))
+        atomicAdd(&p.cnt->st[ST_AMBIG], 1ull);
+    }
   }
   if (make_leaf) {
     if (tid == 0) {
@@ -1228,7 +1463,14 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
     } else if (TASK == TASK_CLSW) {
       for (int c = tid; c < C; c += TEAM) lv[c] = s_dist[c];
     } else {
-      if (tid == 0) lv[0] = leaf_mean;
+      if (tid == 0) {
+        if (REGPAR) {  // a large leaf is rare: its value is the reference's sequential mean (pkg:782), exactly
+          double sum = 0.0;
+          for (int32_t j = 0; j < n; j++) sum = ET_ADD(sum, yy[j]);
+          leaf_mean = ET_DIV(sum, (double)n);
+        }
+        lv[0] = leaf_mean;
+      }
     }
     return;
   }
@@ -1631,10 +1873,19 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? 6 : 4) k_lane(P p, in
       if (p.replay) {
         nb = min(32, tcnt - tpos);
       } else {
-        // over-draw (about half of the draws hit constants on sparse tables); candidates past the k-th
-        // scored one are discarded unexamined below, like the reference which stops drawing there
+        // over-draw by the share of constant features expected among the draws: observed at this node once a
+        // batch has been examined; before that, one in two if constants were found on the path from the root
+        // (sparse tables) and none otherwise (continuous tables never waste a gather).  Candidates past the k-th
+        // scored one are discarded unexamined below, like the reference which stops drawing there.
         const int32_t need = min(p.k - visited, avail);
-        nb = (need > 0) ? min(32, min(avail, 2 * need + 4)) : 0;
+        int32_t extra;
+        if (st_draws > 0)
+          extra = (st_draws > (unsigned long long)visited)
+                      ? (int32_t)(((long long)need * (long long)(st_draws - (unsigned long long)visited)) / max(visited, 1)) + 2
+                      : 0;
+        else
+          extra = (nconst > 0) ? need + 4 : 0;
+        nb = (need > 0) ? min(32, min(avail, need + extra)) : 0;
       }
       if (nb <= 0) break;
       // ---- draw: lane == candidate
@@ -2506,6 +2757,8 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       S.const_hits += (int64_t)hc.st[ST_CONST];
       S.scored += (int64_t)hc.st[ST_SCORED];
       S.replay_mismatches += (int64_t)hc.st[ST_MISMATCH];
+      S.parallel_sum_nodes += (int64_t)hc.st[ST_PARNODES];
+      S.ambiguous_splits += (int64_t)hc.st[ST_AMBIG];
       S.nodes += n_nodes;
       // ---- creation order -> per-tree pre-order, on the device
       pt.start();
