@@ -593,7 +593,9 @@ __device__ __forceinline__ void coded_pass2(const uint8_t *__restrict__ C8, cons
 
 template <int TASK, int TEAM, bool CODED>
 __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
-                                  TEAM == 32 ? 5 : (TEAM == MID_TEAM ? (CODED ? 4 : 6) : 2))
+                                  TEAM == 32 ? 5
+                                             : (TEAM == MID_TEAM ? (CODED ? 4 : 6)
+                                                                 : ((TASK == TASK_REG && TEAM == CTA_TEAM) ? 1 : 2)))
     k_node(P p, int32_t qcount, int qi) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool WARP = (TEAM == 32);
@@ -907,16 +909,29 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
               mn[c] = 1.7976931348623157e308;  // pkg:35-36
               mx[c] = -1.7976931348623157e308;
             }
-            for (int32_t j = tid; j < n; j += TEAM) {
-              const int32_t r = rr[j];
-              double x[4];
+            // four samples per thread and trip: 16 independent gathers in flight
+            for (int32_t j0 = tid; j0 < n; j0 += 4 * TEAM) {
+              int32_t r[4];
+              double x[4][4];
 #pragma unroll
-              for (int c = 0; c < 4; c++) x[c] = __ldg(colp[c] + r);
+              for (int u2 = 0; u2 < 4; u2++) {
+                const int32_t j = j0 + u2 * TEAM;
+                r[u2] = (j < n) ? rr[j] : -1;
+              }
 #pragma unroll
-              for (int c = 0; c < 4; c++) {
-                if (x[c] < mn[c]) mn[c] = x[c];
-                if (x[c] > mx[c]) mx[c] = x[c];
-                nanm |= (uint32_t)(x[c] != x[c]) << c;
+              for (int u2 = 0; u2 < 4; u2++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) x[u2][c] = (r[u2] >= 0) ? __ldg(colp[c] + r[u2]) : 0.0;
+#pragma unroll
+              for (int u2 = 0; u2 < 4; u2++) {
+                if (r[u2] >= 0) {
+#pragma unroll
+                  for (int c = 0; c < 4; c++) {
+                    if (x[u2][c] < mn[c]) mn[c] = x[u2][c];
+                    if (x[u2][c] > mx[c]) mx[c] = x[u2][c];
+                    nanm |= (uint32_t)(x[u2][c] != x[u2][c]) << c;
+                  }
+                }
               }
             }
 #pragma unroll
@@ -978,18 +993,29 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
               S[c] = 0.0;
               Q[c] = 0.0;
             }
-            for (int32_t j = tid; j < n; j += TEAM) {
-              const int32_t r = rr[j];
-              double x[4];
+            for (int32_t j0 = tid; j0 < n; j0 += 4 * TEAM) {
+              int32_t r[4];
+              double x[4][4], yd[4];
 #pragma unroll
-              for (int c = 0; c < 4; c++) x[c] = __ldg(colp[c] + r);
-              const double yd = ET_SUB(yy[j], reg_mu), yd2 = ET_MUL(yd, yd);
+              for (int u2 = 0; u2 < 4; u2++) {
+                const int32_t j = j0 + u2 * TEAM;
+                r[u2] = (j < n) ? rr[j] : -1;
+                yd[u2] = (j < n) ? ET_SUB(yy[j], reg_mu) : 0.0;
+              }
 #pragma unroll
-              for (int c = 0; c < 4; c++) {
-                const bool in = sweep ? (x[c] != x[c]) : (x[c] < cut[c]);
-                cnt[c] += in ? 1 : 0;
-                S[c] = ET_ADD(S[c], in ? yd : 0.0);
-                Q[c] = ET_ADD(Q[c], in ? yd2 : 0.0);
+              for (int u2 = 0; u2 < 4; u2++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) x[u2][c] = (r[u2] >= 0) ? __ldg(colp[c] + r[u2]) : 0.0;
+#pragma unroll
+              for (int u2 = 0; u2 < 4; u2++) {
+                const double yd2 = ET_MUL(yd[u2], yd[u2]);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                  const bool in = (r[u2] >= 0) && (sweep ? (x[u2][c] != x[u2][c]) : (x[u2][c] < cut[c]));
+                  cnt[c] += in ? 1 : 0;
+                  S[c] = ET_ADD(S[c], in ? yd[u2] : 0.0);
+                  Q[c] = ET_ADD(Q[c], in ? yd2 : 0.0);
+                }
               }
             }
 #pragma unroll
