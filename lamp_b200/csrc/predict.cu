@@ -43,17 +43,40 @@ __global__ void __launch_bounds__(256) k_predict(const PNode *__restrict__ nodes
   for (int32_t t0 = 0; t0 < m; t0 += TB) {
     const int32_t tb = min(TB, m - t0);
     if (has_row) {
-      for (int32_t t = sl; t < tb; t += TS) {
-        const PNode *tn = nodes + tree_off[t0 + t];
-        int32_t id = 0;
-        PNode pn = tn[0];
-        while (pn.feat >= 0) {
-          const double v = xr[pn.feat & (ET_MIL_BIT - 1)];
-          const bool left = (v < pn.cut) || ((pn.feat & ET_MIL_BIT) && (v != v));
-          id = left ? id + 1 : pn.right_or_leaf;
-          pn = tn[id];
+      // four walks per thread in flight: the pointer chases of different trees are independent, so their node
+      // fetches overlap (a walk is one dependent L2 access per level)
+      for (int32_t t = sl; t < tb; t += 4 * TS) {
+        const PNode *tn[4];
+        PNode pn[4];
+        int32_t id[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int32_t tu = t + u * TS;
+          tn[u] = nodes + tree_off[t0 + (tu < tb ? tu : t)];
+          id[u] = 0;
         }
-        s_leaf[r * TB + t] = pn.right_or_leaf;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          pn[u] = tn[u][0];
+          if (t + u * TS >= tb) pn[u].feat = -1;  // no such tree: the slot is idle
+        }
+        bool more = true;
+        while (more) {
+          more = false;
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if (pn[u].feat >= 0) {
+              const double v = xr[pn[u].feat & (ET_MIL_BIT - 1)];
+              const bool left = (v < pn[u].cut) || ((pn[u].feat & ET_MIL_BIT) && (v != v));
+              id[u] = left ? id[u] + 1 : pn[u].right_or_leaf;
+              pn[u] = tn[u][id[u]];
+              more = true;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (t + u * TS < tb) s_leaf[r * TB + t + u * TS] = pn[u].right_or_leaf;
       }
     }
     __syncthreads();
@@ -62,7 +85,8 @@ __global__ void __launch_bounds__(256) k_predict(const PNode *__restrict__ nodes
       if (row0 + rr < n) {
         double a = s_acc[q];
         const int32_t *lf = s_leaf + rr * TB;
-        for (int32_t t = 0; t < tb; t++) a = ET_ADD(a, leaves[(int64_t)lf[t] * lw + c]);
+#pragma unroll 8
+        for (int32_t t = 0; t < tb; t++) a = ET_ADD(a, leaves[(int64_t)lf[t] * lw + c]);  // (loads run ahead of the adds)
         s_acc[q] = a;
       }
     }
