@@ -28,6 +28,7 @@
 // thread per candidate) because FP addition is not associative.
 #include <algorithm>
 #include <chrono>
+#include <type_traits>
 
 #include "internal.h"
 
@@ -182,6 +183,7 @@ struct P {
   int64_t ldc;
   const double *dict;  // [d][256]
   const uint8_t *coff; // [d] stored byte + coff = wide code (0 NaN, r + 1 for dict[r])
+  int32_t c8_small;    // the coded table is smaller than 4 GiB: gathers use 32-bit offsets from C8
   int32_t cls_max[NQ - 1];
 };
 
@@ -1950,10 +1952,19 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? 6 : 4) k_lane(P p, in
       const bool nan_cols = CODED ? (__any_sync(FULL, K != 0u) != 0) : true;  // can any lane's column hold a NaN?
       uint32_t mnt = 0xffffffffu, mxb = 0u;
       // (one gather per sample and lane; a full chunk keeps all 32 gathers of a lane in flight)
-      auto visit = [&](int32_t rj, int pos) {
+      // byte codes are parked four positions to a word, [position / 4][lane][position % 4]: pass 2 reads one word
+      // per four samples.  The gather address is a 32-bit offset from the table base (host-checked: the coded
+      // table is smaller than 4 GiB, else the 64-bit form is used).
+      const uint8_t *c8base = CODED ? p.C8 : nullptr;
+      const uint32_t coloff32 = (CODED && p.c8_small) ? (uint32_t)((int64_t)(act0 ? f : 0) * p.ldc) : 0u;
+      uint8_t *s_xb = reinterpret_cast<uint8_t *>(s_x);
+      // (inactive lanes gather from column 0: no predicate, no branch, so all gathers of a chunk stay in flight)
+      auto visit = [&](auto small_tab, int32_t rj, int pos) {
         if (CODED) {
-          const uint32_t b8 = act0 ? (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(col) + rj) : 0u;
-          s_x[pos * 32 + lane] = (VT)b8;
+          const uint32_t b8 = decltype(small_tab)::value
+                                  ? (uint32_t)__ldg(c8base + (coloff32 + (uint32_t)rj))
+                                  : (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(col) + rj);
+          s_xb[(((pos >> 2) * 32 + lane) << 2) + (pos & 3)] = (uint8_t)b8;
           mxb = max(mxb, b8);
           mnt = min(mnt, b8 - K);
         } else {
@@ -1964,17 +1975,23 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? 6 : 4) k_lane(P p, in
           has_nan |= (x != x);
         }
       };
-      for (int w = 0; w < nw; w++) {
-        const int j0 = w << 5, cnt = min(32, n - j0);
-        const int32_t row = (lane < cnt) ? idx[j0 + lane] : 0;
-        if (cnt == 32) {
+      auto pass1 = [&](auto small_tab) {
+        for (int w = 0; w < nw; w++) {
+          const int j0 = w << 5, cnt = min(32, n - j0);
+          const int32_t row = (lane < cnt) ? idx[j0 + lane] : 0;
+          if (cnt == 32) {
 #pragma unroll
-          for (int jj = 0; jj < 32; jj++) visit(__shfl_sync(FULL, row, jj), j0 + jj);
-        } else {
+            for (int jj = 0; jj < 32; jj++) visit(small_tab, __shfl_sync(FULL, row, jj), j0 + jj);
+          } else {
 #pragma unroll 4
-          for (int jj = 0; jj < cnt; jj++) visit(__shfl_sync(FULL, row, jj), j0 + jj);
+            for (int jj = 0; jj < cnt; jj++) visit(small_tab, __shfl_sync(FULL, row, jj), j0 + jj);
+          }
         }
-      }
+      };
+      if (CODED && p.c8_small)
+        pass1(std::true_type{});
+      else
+        pass1(std::false_type{});
       uint32_t thr = 0u;
       const uint32_t wmax = CODED ? ((K == 1u) ? mxb : mxb + 1u) : 0u;  // largest wide code; 0 = only NaNs
       if (CODED) {
@@ -2006,17 +2023,26 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? 6 : 4) k_lane(P p, in
         const int j0 = w << 5, cnt = min(32, n - j0);
         uint32_t lt = 0u, nn = 0u;
         if (CODED) {
-          if (nan_cols) {
-#pragma unroll 8
-            for (int jj = 0; jj < cnt; jj++) {
-              const uint32_t t = (uint32_t)s_x[(j0 + jj) * 32 + lane] - K;
-              lt |= (uint32_t)(t < thr) << jj;
-              nn |= (uint32_t)(t == 0xffffffffu) << jj;
+          // four samples per word: t = byte - K bytewise (NaN -> 255), left iff t <= thr - 1 (thr > 0)
+          const uint32_t *s_xw = reinterpret_cast<const uint32_t *>(s_x) + (w * 8) * 32 + lane;
+          const uint32_t K4 = K * 0x01010101u, t4 = (thr > 0u ? thr - 1u : 0u) * 0x01010101u;
+          const uint32_t en4 = thr > 0u ? 0xffffffffu : 0u, kn4 = K ? 0xffffffffu : 0u;
+          const int nq = (cnt + 3) >> 2;
+#pragma unroll
+          for (int q4 = 0; q4 < 8; q4++) {
+            if (q4 < nq) {
+              const uint32_t b4 = s_xw[q4 * 32];
+              const uint32_t l4 = __vcmpleu4(__vsub4(b4, K4), t4) & en4;
+              lt |= (((l4 & 0x01010101u) * 0x01020408u) >> 24) << (4 * q4);
+              if (nan_cols) {
+                const uint32_t n4 = __vcmpeq4(b4, 0u) & kn4;
+                nn |= (((n4 & 0x01010101u) * 0x01020408u) >> 24) << (4 * q4);
+              }
             }
-          } else {
-#pragma unroll 8
-            for (int jj = 0; jj < cnt; jj++) lt |= (uint32_t)((uint32_t)s_x[(j0 + jj) * 32 + lane] < thr) << jj;
           }
+          const uint32_t valid = (cnt >= 32) ? FULL : ((1u << cnt) - 1u);  // (the last word may hold stale bytes)
+          lt &= valid;
+          nn &= valid;
         } else {
 #pragma unroll 8
           for (int jj = 0; jj < cnt; jj++) {
@@ -2685,6 +2711,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       p.ldc = D->ldc;
       p.dict = D->dict;
       p.coff = D->coff;
+      p.c8_small = ((uint64_t)D->ldc * (uint64_t)d < ((uint64_t)1 << 32)) ? 1 : 0;
       p.cls_max[0] = NT_MAX;
       for (int q = 1; q < Q_WARP; q++) p.cls_max[q] = lc.coded ? (NT_MAX << q) : NT_MAX;
       p.cls_max[Q_WARP] = NW_MAX;
