@@ -122,6 +122,10 @@ def test_replay_synthetic_regression(nan_frac, max_depth, n_min):
     gf = et.buildForestRegression(x, y, n_min, 4, 5, 3, maxDepth=max_depth, seed=8, replay=oracle_replay(of))
     assert_trees_bit_exact(gf, of)
     assert np.array_equal(et.predictRegression(gf, x), of.predict(x))
+    # nodes above 2048 samples are scored from fixed-shape parallel sums (not the reference's sequential order):
+    # the structure is still the reference's, and no split was decided by less than 1e-9 (relative)
+    assert gf.stats["parallel_sum_nodes"] > 0
+    assert gf.stats["ambiguous_splits"] == 0
 
 
 # ---- free-running: the reference's own property tests --------------------------------------------------
@@ -235,3 +239,85 @@ def test_packed_export_import_roundtrip(mnist):
         bad["tree_off"] = ser["tree_off"].copy()
         bad["tree_off"][-1] += 1
         et.Forest.import_packed(bad)
+
+
+# ---- byte-coded table: edge cases of the dictionary coding (encode.cu) ------------------------------------
+def _coding_edge_table(with_nan):
+    rng = np.random.default_rng(17)
+    n = 3000
+    x = np.empty((n, 6))
+    x[:, 0] = rng.integers(0, 256, size=n)                      # 256 distinct values: the whole byte range
+    x[:, 1] = rng.choice([-np.inf, -1.5, -0.0, 0.0, 2.5, np.inf], size=n)  # infinities, both zeros
+    x[:, 2] = rng.integers(0, 255, size=n) * 1e-300             # tiny magnitudes (subnormal products)
+    x[:, 3] = 7.0                                               # constant
+    x[:, 4] = rng.integers(0, 3, size=n)                        # three values
+    x[:, 5] = rng.normal(size=n).round(1)
+    if with_nan:
+        x[rng.random(n) < 0.2, 2] = np.nan                      # 255 values + NaN = 256 codes
+        x[rng.random(n) < 0.5, 4] = np.nan
+    y = ((x[:, 0] > 100).astype(np.int32) + (np.nan_to_num(x[:, 4]) > 0)).astype(np.int32)
+    return x, y
+
+
+@pytest.mark.parametrize("with_nan", [False, True])
+def test_replay_coding_edge_cases(with_nan):
+    x, y = _coding_edge_table(with_nan)
+    of = O.build_forest_classification(x, y, None, 3, 2, 4, 6, 2, seed=31, record_trace=True)
+    gf = et.buildForestClassification(x, y, None, 3, 2, 4, 6, 2, seed=31, replay=oracle_replay(of))
+    assert_trees_bit_exact(gf, of)
+    assert np.array_equal(et.predictClassification(gf, x), of.predict(x))
+    yr = y + 0.25 * x[:, 5]
+    of = O.build_forest_regression(x, yr, 3, 4, 4, 2, seed=32, record_trace=True)
+    gf = et.buildForestRegression(x, yr, 3, 4, 4, 2, seed=32, replay=oracle_replay(of))
+    assert_trees_bit_exact(gf, of)
+
+
+# ---- BASELINE.json sizes: size-independent properties --------------------------------------------------------
+def test_full_size_mnist_shaped_properties(table_coding):
+    """configs[1] at full size (60000 x 784, 10 classes; the bench generator): every fully grown tree (nMin=2)
+    reproduces its training labels, its leaves are one-hot, it is a proper pre-order binary tree, and the forest
+    vote is the mean of the per-tree votes."""
+    import bench
+    cfg = bench.CONFIGS["mnist"]
+    x, y = bench.make_data(cfg)
+    m = 8
+    f = et.buildForestClassification(x, y, None, cfg["C"], cfg["n_min"], cfg["k"], m, 8, seed=77)
+    ser = f.export_packed()
+    nodes, leaves, off = ser["nodes"], ser["leaves"], ser["tree_off"]
+    split = nodes["feat"] >= 0
+    assert split.sum() + 1 * m == (~split).sum()              # a binary tree has one more leaf than splits
+    assert len(leaves) == (~split).sum()
+    # (a pure leaf of s samples holds 1/s added s times, pkg:905-911: one-hot up to the last bits)
+    assert np.all((leaves == 0.0) | (np.abs(leaves - 1.0) < 1e-12)) and np.all(np.abs(leaves.sum(axis=1) - 1.0) < 1e-12)
+    assert np.array_equal(np.sort(nodes["right_or_leaf"][~split]), np.arange(len(leaves)))
+    for t in range(m):
+        nt = nodes[off[t]:off[t + 1]]
+        s = nt["feat"] >= 0
+        idx = np.nonzero(s)[0]
+        assert np.all(nt["right_or_leaf"][s] > idx + 1) and np.all(nt["right_or_leaf"][s] < len(nt))
+        assert np.all((nt["feat"][s] & 0x3FFFFFFF) < cfg["d"])
+    votes = et.predictClassification(f, x)
+    assert np.array_equal(votes.argmax(1), y)                  # (no two identical rows carry different labels)
+    one = et.Forest.import_packed(dict(ser, nodes=nodes[off[0]:off[1]], tree_off=off[:2] - off[0]))
+    p0 = et.predictClassification(one, x[:2000])
+    assert np.all(np.abs(p0.sum(axis=1) - 1.0) < 1e-12) and np.array_equal(p0.argmax(1), y[:2000])
+    assert np.allclose(votes.sum(axis=1), 1.0, atol=1e-12)
+    if table_coding == "codes":
+        assert f.stats["launches"] > 0 and f.stats["v_mm"] >= f.stats["v_sc"] > 0
+
+
+def test_full_size_regression_properties():
+    """configs[2] shape at 1/4 of the rows (250000 x 100, continuous features): trees are proper, leaf means lie
+    inside the target range, nodes of more than 2048 samples took the parallel-sum path, and the fit beats the
+    constant predictor by a wide margin."""
+    import bench
+    x, y = bench.gen_regression(250_000, 100, 3)
+    f = et.buildForestRegression(x, y, 5, 10, 4, 8, seed=9)
+    ser = f.export_packed()
+    nodes, leaves = ser["nodes"], ser["leaves"]
+    split = nodes["feat"] >= 0
+    assert split.sum() + 4 == (~split).sum()
+    assert leaves.min() >= y.min() and leaves.max() <= y.max()
+    assert f.stats["parallel_sum_nodes"] > 0
+    pred = et.predictRegression(f, x[:50_000])
+    assert np.mean((pred - y[:50_000]) ** 2) < 0.2 * np.var(y)
