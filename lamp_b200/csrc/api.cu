@@ -105,13 +105,20 @@ extern "C" int et_init(int32_t device, et_ctx **out) {
   et_ctx *c = new et_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  CUDA_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  // the level loop (own stream + the side streams of its size classes) runs at high priority; the asynchronous
+  // resident-subtree kernels run on low-priority streams and fill the SMs the level loop leaves idle
+  int prio_least = 0, prio_greatest = 0;
+  CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  CUDA_CHECK(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, prio_greatest));
   c->stream = c->own_stream;
   CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-  for (int i = 0; i < 7; i++) {
-    CUDA_CHECK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+  for (int i = 0; i < et_ctx::N_SIDE; i++) {
+    CUDA_CHECK(cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, prio_greatest));
     CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
   }
+  for (int q = 0; q < et_ctx::N_SUB_CLS; q++)
+    for (int r = 0; r < et_ctx::N_SUB_RING; r++)
+      CUDA_CHECK(cudaStreamCreateWithPriority(&c->sub_stream[q][r], cudaStreamNonBlocking, prio_least));
   *out = c;
   ET_API_END
 }
@@ -121,11 +128,14 @@ extern "C" void et_shutdown(et_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
-  for (int i = 0; i < 7; i++) {
+  for (int i = 0; i < et_ctx::N_SIDE; i++) {
     if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
     if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (int q = 0; q < et_ctx::N_SUB_CLS; q++)
+    for (int r = 0; r < et_ctx::N_SUB_RING; r++)
+      if (ctx->sub_stream[q][r]) cudaStreamDestroy(ctx->sub_stream[q][r]);
   et_workspace_free(ctx->ws);
   for (auto &b : ctx->cache) cudaFree(b.p);
   delete ctx;

@@ -53,17 +53,24 @@ constexpr int CBIG_TEAM = 256;    // threads of the CTA that owns a larger node 
 constexpr int WARPS_PER_CTA = 4;  // warp teams per CTA in the small-node kernel
 
 // Size classes of the open nodes (upper bounds in P::cls_max; an empty class repeats its predecessor's bound):
-//   0..4  n <= 32, 64, 128, 256, 512: one warp per node, one lane per candidate (k_lane; classes 1..4 only
-//         on byte-coded tables, each with shared memory sized to its bound)
-//   4     (FP64 tables) n <= 512: one warp per node, lanes on samples (k_node<32>)
-//   5, 6  n <= 2048, larger: one CTA per node (k_node)
-constexpr int NQ = 7;
-constexpr int Q_WARP = 4, Q_MID = 5, Q_CTA = 6;
+//   0..4  resident subtrees (subtree.cuh) when the row-major copy of the table exists and a useful number of
+//         rows fits one SM: n <= rw * {1, 2, 4, 8, 16}, built to the leaves by teams of 1..16 warps (k_sub);
+//         otherwise n <= 32, 64, 128, 256, 512: one warp per node, one lane per candidate (k_lane; classes
+//         1..4 only on byte-coded tables, each with shared memory sized to its bound)
+//         (empty when the subtree builder is off)
+//   5..9  n <= 32, 64, 128, 256, 512: one warp per node, one lane per candidate (k_lane; classes 6..9 only on
+//         byte-coded tables, each with shared memory sized to its bound); FP64 tables: class 9 = n <= 512, one
+//         warp per node with lanes on samples (k_node<32>)
+//   10, 11  n <= 2048, larger: one CTA per node (k_node)
+constexpr int NQ = 12;
+constexpr int Q_LANE0 = 5, Q_WARP = 9, Q_MID = 10, Q_CTA = 11;
 
 struct Counters {
   int32_t next_f;
   int32_t q_count[NQ];
+  int32_t sub_rows;  // rows of the nodes queued for the resident subtree builder at the next level
   int32_t n_leaves;
+  unsigned int sub_nodes;  // nodes written to the subtree block pool so far
   unsigned long long scratch_words;
   unsigned long long st[ST_COUNT];
 };
@@ -185,6 +192,12 @@ struct P {
   const uint8_t *coff; // [d] stored byte + coff = wide code (0 NaN, r + 1 for dict[r])
   int32_t c8_small;    // the coded table is smaller than 4 GiB: gathers use 32-bit offsets from C8
   int32_t cls_max[NQ - 1];
+  // resident subtree builder (subtree.cuh)
+  const uint8_t *R8;   // row-major byte codes [n][sub_rowbytes]
+  const double *XR;    // row-major FP64 [n][sub_rowbytes / 8]
+  int32_t sub_ncls;    // size classes 0 .. sub_ncls - 1 are built by k_sub (0: off)
+  int32_t sub_rw, sub_rowbytes;  // staged rows per warp, bytes per staged row
+  PNode *sub_nodes;    // block pool: pre-order blocks of finished subtrees
 };
 
 __host__ __device__ inline int size_class(const P &p, int64_t n) {
@@ -1527,6 +1540,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
       const int32_t cn = side ? (n - nl) : nl;
       const int qc = size_class(p, cn);
       p.q_nxt[qc][atomicAdd(&p.cnt->q_count[qc], 1)] = s2;
+      if (qc < p.sub_ncls) atomicAdd(&p.cnt->sub_rows, cn);
     }
     atomicAdd(&p.cnt->st[ST_PROWS], (unsigned long long)n);
   }
@@ -2188,6 +2202,7 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? 6 : 4) k_lane(P p, in
       p.nxt.trace[s2] = tc;
       const int qc = size_class(p, side ? (n - nl) : nl);  // (these classes compute their own class histogram)
       p.q_nxt[qc][atomicAdd(&p.cnt->q_count[qc], 1)] = s2;
+      if (qc < p.sub_ncls) atomicAdd(&p.cnt->sub_rows, side ? (n - nl) : nl);
     }
     atomicAdd(&p.cnt->st[ST_PROWS], (unsigned long long)n);
   }
@@ -2229,11 +2244,17 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? 6 : 4) k_lane(P p, in
 }
 #undef LANE_IN
 
+#include "subtree.cuh"
+
 // ---- pool (creation order) -> per-tree pre-order ----------------------------------------------
 __global__ void k_subtree_sizes(Pool o, int32_t lo, int32_t hi, int32_t *size, int32_t *nleaf) {
   int v = lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= hi) return;
-  if (o.feat[v] < 0) {
+  if (o.feat[v] == SUB_MARK) {  // a finished resident subtree: (nodes, leaves) ride in the cut field
+    const unsigned long long packed = (unsigned long long)__double_as_longlong(o.cut[v]);
+    size[v] = (int32_t)(packed & 0xffffffffu);
+    nleaf[v] = (int32_t)(packed >> 32);
+  } else if (o.feat[v] < 0) {
     size[v] = 1;
     nleaf[v] = 1;
   } else {
@@ -2279,6 +2300,7 @@ __global__ void k_scatter(Pool o, int32_t n_nodes, int lw, const int32_t *pos, c
                           PNode *nodes, double *leaves) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_nodes) return;
+  if (o.feat[v] == SUB_MARK) return;  // k_scatter_sub places the whole block
   const int t = o.tree[v];
   PNode pn;
   const int64_t g = tree_off[t] - node_base + pos[v];
@@ -2309,11 +2331,21 @@ static T *upload_tmp(const T *h, size_t n, cudaStream_t st) {
   return d;
 }
 
+// The frontier (and its queues) of level L lives in slot L % FR_RING.  The resident subtree kernels of a level run
+// asynchronously to the level loop and read their slot when their CTAs start, so a slot is only rewritten
+// FR_RING - 1 levels later, after those kernels have finished (event wait in launch_level).
+constexpr int FR_RING = 4;
+static_assert(FR_RING == et_ctx::N_SUB_RING, "one subtree stream per ring slot");
+
 struct FrontierBufs {
   DevBuf<int32_t> tree, begin, end, node, depth, hist;
   DevBuf<int64_t> trace;
   DevBuf<uint64_t> key;
   DevBuf<uint32_t> mask;
+  bool fits(size_t F, int C, int W, bool need_hist, bool need_mask) const {
+    return tree.cap >= F && begin.cap >= F && end.cap >= F && node.cap >= F && depth.cap >= F && trace.cap >= F &&
+           key.cap >= F && (!need_hist || hist.cap >= F * (size_t)C) && (!need_mask || mask.cap >= F * (size_t)W);
+  }
   void ensure(size_t F, int C, int W, bool need_hist, bool need_mask) {
     tree.ensure(F, 1.5);
     begin.ensure(F, 1.5);
@@ -2331,6 +2363,9 @@ struct FrontierBufs {
 struct PoolBufs {
   DevBuf<int32_t> tree, feat, child;
   DevBuf<double> cut, leaf_vals;
+  bool fits(size_t n, size_t nleaf, int lw) const {
+    return tree.cap >= n && feat.cap >= n && child.cap >= n && cut.cap >= n && leaf_vals.cap >= nleaf * (size_t)lw;
+  }
   void grow(size_t n, size_t used, size_t nleaf, size_t leaf_used, int lw, cudaStream_t st) {
     tree.grow_keep(n, used, st);
     feat.grow_keep(n, used, st);
@@ -2345,11 +2380,12 @@ struct PoolBufs {
 
 // Device buffers that survive across builds on one context (no cudaMalloc in the steady state).
 struct Workspace {
-  DevBuf<int32_t> idx[2], yc[2], q[2][NQ], size, nleaf, pos, lpos;
+  DevBuf<int32_t> idx[2], yc[2], q[FR_RING][NQ], size, nleaf, pos, lpos;
   DevBuf<double> yr[2], ws[2];
-  FrontierBufs fr[2];
+  FrontierBufs fr[FR_RING];
   PoolBufs pool;
   DevBuf<uint32_t> scratch;
+  DevBuf<PNode> sub_nodes;  // block pool of the resident subtree builder
   DevBuf<Counters> cnt;
   DevBuf<int64_t> tree_off, leaf_off;
 };
@@ -2364,9 +2400,9 @@ struct PhaseTimer {
   double last[8] = {0};
   void level_report(int level, const int32_t *qn) {
     if (!per_level) return;
-    fprintf(stderr, "[etgpu level %3d] nodes n32=%d n64=%d n128=%d n256=%d n512=%d mid=%d cta=%d | ms tiny=%.3f warp=%.3f mid=%.3f cta=%.3f\n",
-            level, qn[0], qn[1], qn[2], qn[3], qn[4], qn[5], qn[6], acc[7] - last[7], acc[2] - last[2], acc[6] - last[6],
-            acc[3] - last[3]);
+    fprintf(stderr, "[etgpu level %3d] nodes sub=%d,%d,%d,%d,%d n32=%d n64=%d n128=%d n256=%d n512=%d mid=%d cta=%d | ms sub=%.3f warp=%.3f mid=%.3f cta=%.3f\n",
+            level, qn[0], qn[1], qn[2], qn[3], qn[4], qn[5], qn[6], qn[7], qn[8], qn[9], qn[10], qn[11], acc[7] - last[7],
+            acc[2] - last[2], acc[6] - last[6], acc[3] - last[3]);
     for (int i = 0; i < 8; i++) last[i] = acc[i];
   }
   cudaStream_t st;
@@ -2384,7 +2420,7 @@ struct PhaseTimer {
   }
   void report() {
     if (!on) return;
-    static const char *names[] = {"alloc", "init", "node_warp", "node_cta", "sync", "preorder", "node_mid", "node_tiny"};
+    static const char *names[] = {"alloc", "init", "node_warp", "node_cta", "sync", "preorder", "node_mid", "node_sub"};
     fprintf(stderr, "[etgpu timing ms]");
     for (int i = 0; i < 8; i++) fprintf(stderr, " %s=%.1f", names[i], acc[i]);
     fprintf(stderr, "\n");
@@ -2426,7 +2462,32 @@ struct LevelCfg {
   bool coded_big;  // larger nodes: byte-coded CTA teams (unweighted classification, <= 32 classes)
   size_t smem_warp, smem_mid, smem_cta;  // k_node teams (per team)
   size_t smem_lane[5];                   // k_lane per warp, classes 0..4
+  int sub_ncls = 0;                      // classes 0 .. sub_ncls - 1: resident subtrees (k_sub), team width 1 << class
+  int sub_rw = 0, sub_rowbytes = 0;
+  size_t smem_sub[SUB_NCLS] = {0};       // k_sub per CTA
 };
+
+template <int TASK, typename VT>
+void launch_sub(et_ctx *ctx, const P &p, int32_t count, int q, const LevelCfg &lc, cudaStream_t st) {
+  const unsigned grid = (unsigned)count;  // one CTA (team) per subtree
+  switch (q) {
+    case 0: k_sub<TASK, VT, 1><<<grid, 32, lc.smem_sub[0], st>>>(p, count, q); break;
+    case 1: k_sub<TASK, VT, 2><<<grid, 64, lc.smem_sub[1], st>>>(p, count, q); break;
+    case 2: k_sub<TASK, VT, 4><<<grid, 128, lc.smem_sub[2], st>>>(p, count, q); break;
+    case 3: k_sub<TASK, VT, 8><<<grid, 256, lc.smem_sub[3], st>>>(p, count, q); break;
+    default: k_sub<TASK, VT, 16><<<grid, 512, lc.smem_sub[4], st>>>(p, count, q); break;
+  }
+  ctx->launches++;
+}
+
+template <int TASK, typename VT>
+void set_sub_attr(const LevelCfg &lc) {
+  CUDA_CHECK(cudaFuncSetAttribute(k_sub<TASK, VT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem_sub[0]));
+  CUDA_CHECK(cudaFuncSetAttribute(k_sub<TASK, VT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem_sub[1]));
+  CUDA_CHECK(cudaFuncSetAttribute(k_sub<TASK, VT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem_sub[2]));
+  CUDA_CHECK(cudaFuncSetAttribute(k_sub<TASK, VT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem_sub[3]));
+  CUDA_CHECK(cudaFuncSetAttribute(k_sub<TASK, VT, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem_sub[4]));
+}
 
 template <int TASK, typename VT>
 void launch_lane(et_ctx *ctx, const P &p, int32_t count, int qi, int NW, size_t smem_per_warp, cudaStream_t st) {
@@ -2447,12 +2508,27 @@ void launch_coded_team(const P &p, int32_t count, int qi, size_t smem, cudaStrea
 // One level = one launch per non-empty size class.  The classes are independent (disjoint nodes), so
 // each runs on its own stream: the few long-running CTAs of the large nodes overlap with the many
 // small teams instead of serialising behind them.  (ETGPU_TIMING serialises them to time each.)
+struct SubEvents {  // completion events of the asynchronous subtree kernels, per frontier slot and team class
+  cudaEvent_t ev[FR_RING][SUB_NCLS] = {};
+  bool valid[FR_RING][SUB_NCLS] = {};
+  bool inflight = false;
+};
+
 template <int TASK>
-void launch_level(et_ctx *ctx, const P &p, const int32_t *qn, const LevelCfg &lc, PhaseTimer &pt, EventTimer &et) {
+void launch_level(et_ctx *ctx, const P &p, const int32_t *qn, const LevelCfg &lc, PhaseTimer &pt, EventTimer &et,
+                  SubEvents &se, int slot_cur, int slot_nxt) {
   cudaStream_t main_st = ctx->stream;
   const bool fork = !pt.on;
+  const bool async_sub = !pt.on && lc.sub_ncls > 0;
+  // this level rewrites frontier slot `slot_nxt`: the subtree kernels that read it last must have finished
+  for (int q = 0; q < SUB_NCLS; q++) {
+    if (se.valid[slot_nxt][q]) {
+      cudaStreamWaitEvent(main_st, se.ev[slot_nxt][q], 0);
+      se.valid[slot_nxt][q] = false;
+    }
+  }
   int used = 0;
-  for (int q = 0; q < NQ; q++) used += (qn[q] > 0);
+  for (int q = 0; q < NQ; q++) used += (qn[q] > 0 && !(async_sub && q < lc.sub_ncls));
   const int e0 = et.rec(main_st);
   if (fork && used > 1) cudaEventRecord(ctx->ev_fork, main_st);
   bool joined[NQ] = {false};
@@ -2489,18 +2565,37 @@ void launch_level(et_ctx *ctx, const P &p, const int32_t *qn, const LevelCfg &lc
   }
   for (int q = Q_WARP; q >= 0; q--) {
     if (qn[q] <= 0) continue;
+    if (async_sub && q < lc.sub_ncls) {
+      // resident subtrees produce nothing the next level needs: their stream is not joined at the level end
+      // (everything they read was finished before the host launched this level)
+      cudaStream_t sst = ctx->sub_stream[q][slot_cur];
+      if (lc.coded)
+        launch_sub<TASK, uint8_t>(ctx, p, qn[q], q, lc, sst);
+      else
+        launch_sub<TASK, double>(ctx, p, qn[q], q, lc, sst);
+      cudaEventRecord(se.ev[slot_cur][q], sst);
+      se.valid[slot_cur][q] = true;
+      se.inflight = true;
+      continue;
+    }
     pt.start();
     cudaStream_t st = stream_for(q);
-    if (lc.coded) {
-      launch_lane<TASK, uint8_t>(ctx, p, qn[q], q, 1 << q, lc.smem_lane[q], st);
-    } else if (q == 0) {
+    if (q < lc.sub_ncls) {
+      if (lc.coded)
+        launch_sub<TASK, uint8_t>(ctx, p, qn[q], q, lc, st);
+      else
+        launch_sub<TASK, double>(ctx, p, qn[q], q, lc, st);
+    } else if (lc.coded) {
+      const int cq = q - Q_LANE0;
+      launch_lane<TASK, uint8_t>(ctx, p, qn[q], q, 1 << cq, lc.smem_lane[cq], st);
+    } else if (q == Q_LANE0) {
       launch_lane<TASK, double>(ctx, p, qn[q], q, 1, lc.smem_lane[0], st);
-    } else {  // FP64 tables: only class Q_WARP is populated besides class 0
+    } else {  // FP64 tables: only class Q_WARP is populated besides class Q_LANE0 (and the subtree classes)
       k_node<TASK, 32, false>
           <<<(unsigned)ceil_div(qn[q], WARPS_PER_CTA), 32 * WARPS_PER_CTA, lc.smem_warp * WARPS_PER_CTA, st>>>(p, qn[q], q);
       ctx->launches++;
     }
-    pt.stop(q == 0 ? 7 : 2);
+    pt.stop(q < lc.sub_ncls ? 7 : 2);
   }
   for (int i = 0; i < NQ; i++) {
     if (joined[i]) {
@@ -2538,6 +2633,12 @@ void set_smem_attr(const LevelCfg &lc) {
                                     (int)(lc.smem_lane[0] * LANE_WARPS)));
     CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(lc.smem_warp * WARPS_PER_CTA)));
+  }
+  if (lc.sub_ncls > 0) {
+    if (lc.coded)
+      set_sub_attr<TASK, uint8_t>(lc);
+    else
+      set_sub_attr<TASK, double>(lc);
   }
 }
 
@@ -2589,6 +2690,39 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
     lc.smem_cta = (size_t)make_lay(task, CBIG_TEAM, C, NB, W, replay, true).bytes;
   }
   if (!lc.coded) lc.smem_lane[0] = (size_t)lane_smem_bytes(task, C, W, replay, 1, 8);
+  // resident subtrees: how many rows of the row-major copy fit one SM next to the teams' scratch
+  {
+    const bool have_rm = lc.coded ? (D->r8 != nullptr) : (D->xr != nullptr);
+    const int64_t rowbytes = lc.coded ? D->rs8 : D->rsd * 8;
+    int smem_max = 0;
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+    // Off unless ETGPU_SUB_NCLS asks for it: measured on B200 the subtree kernels cut the
+    // level loop from 145 to 110 ms on the MNIST-shaped workload but need more SM time for the small nodes than
+    // the gathering kernels they replace, so the build as a whole gets slower.
+    int ncls = 0, rw_cap = 16;
+    if (const char *env = getenv("ETGPU_SUB_NCLS")) ncls = std::max(0, std::min(SUB_NCLS, atoi(env)));
+    if (const char *env = getenv("ETGPU_SUB_RW")) rw_cap = std::max(1, std::min(16, atoi(env)));
+    if (have_rm && ncls > 0 && (task == TASK_REG || C <= 256) && rowbytes < (1 << 20)) {
+      int rw = rw_cap;
+      // a team of 1 << q warps is one CTA; SUB_WARPS >> q of them share an SM (1 KB per CTA is reserved)
+      const size_t sm_total = (size_t)smem_max + 1024;
+      auto fits = [&](int r) {
+        for (int q = 0; q < SUB_NCLS; q++)
+          if ((sub_smem_bytes(task, C, W, replay, 1 << q, r, (int)rowbytes, lc.coded) + 1024) * (size_t)(SUB_WARPS >> q) >
+              sm_total)
+            return false;
+        return true;
+      };
+      while (rw >= 4 && !fits(rw)) rw--;
+      if (rw >= 4) {
+        lc.sub_ncls = ncls;
+        lc.sub_rw = rw;
+        lc.sub_rowbytes = (int)rowbytes;
+        for (int q = 0; q < SUB_NCLS; q++)
+          lc.smem_sub[q] = sub_smem_bytes(task, C, W, replay, 1 << q, rw, (int)rowbytes, lc.coded);
+      }
+    }
+  }
   if (lc.smem_lane[0] * LANE_WARPS > 200 * 1024)
     ET_FAIL(ET_EUNSUPPORTED, "numClasses=%d / %d features need more shared memory per node than one SM has", C, d);
   if (task == TASK_CLS)
@@ -2601,6 +2735,9 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
   cudaEvent_t ev0, ev1;
   CUDA_CHECK(cudaEventCreate(&ev0));
   CUDA_CHECK(cudaEventCreate(&ev1));
+  SubEvents sub_ev;
+  for (int r = 0; r < FR_RING; r++)
+    for (int q = 0; q < SUB_NCLS; q++) CUDA_CHECK(cudaEventCreateWithFlags(&sub_ev.ev[r][q], cudaEventDisableTiming));
   CUDA_CHECK(cudaEventRecord(ev0, st));
 
   // the reference's seeding (pkg:629,654-655) names one stream per tree; the free-running GPU RNG
@@ -2672,6 +2809,9 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
     cudaFree(d_tr_cand_flag);
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
+    for (int r = 0; r < FR_RING; r++)
+      for (int q = 0; q < SUB_NCLS; q++)
+        if (sub_ev.ev[r][q]) cudaEventDestroy(sub_ev.ev[r][q]);
   };
 
   out->m = a.m;
@@ -2712,13 +2852,19 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       p.dict = D->dict;
       p.coff = D->coff;
       p.c8_small = ((uint64_t)D->ldc * (uint64_t)d < ((uint64_t)1 << 32)) ? 1 : 0;
-      p.cls_max[0] = NT_MAX;
-      for (int q = 1; q < Q_WARP; q++) p.cls_max[q] = lc.coded ? (NT_MAX << q) : NT_MAX;
+      for (int q = 0; q < Q_LANE0; q++) p.cls_max[q] = (q < lc.sub_ncls) ? (lc.sub_rw << q) : 0;  // 0: empty class
+      p.cls_max[Q_LANE0] = NT_MAX;
+      for (int q = 1; q < 4; q++) p.cls_max[Q_LANE0 + q] = lc.coded ? (NT_MAX << q) : NT_MAX;
       p.cls_max[Q_WARP] = NW_MAX;
       p.cls_max[Q_MID] = NM_MAX;
+      p.R8 = D->r8;
+      p.XR = D->xr;
+      p.sub_ncls = lc.sub_ncls;
+      p.sub_rw = lc.sub_rw;
+      p.sub_rowbytes = lc.sub_rowbytes;
       p.tr = Trace{d_tr_cand_begin, d_tr_cand_count, d_tr_left, d_tr_right, d_tr_cand_feature, d_tr_cand_u,
                    d_tr_cand_flag};
-      int srcb = 0, cl = 0;
+      int srcb = 0, cl = 0;  // cl: frontier slot of the current level (ring of FR_RING)
       int32_t F = Bt;
       ws.fr[0].ensure((size_t)F, C, W, task == TASK_CLS, !replay);
       for (int q = 0; q < NQ; q++) ws.q[0][q].ensure((size_t)F, 1.5);
@@ -2748,14 +2894,43 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       std::vector<int32_t> level_start{0};
       int32_t qn[NQ] = {0};
       qn[size_class(p, n)] = Bt;
+      int64_t sub_rows_level = (size_class(p, n) < lc.sub_ncls) ? (int64_t)Bt * n : 0;  // rows entering k_sub this level
+      int64_t sub_nodes_used = 0;
+      int64_t leaf_bound = 0, subnode_bound = 0;  // upper bounds of the leaves / block nodes allocated so far
       Counters hc;
       memset(&hc, 0, sizeof(hc));
+      // the asynchronous subtree kernels hold pointers into the pools and the frontier ring: a buffer only moves
+      // after they have drained (never in the steady state, where the workspace is already large enough)
+      auto quiesce = [&]() {
+        if (!sub_ev.inflight) return;
+        for (int q = 0; q < SUB_NCLS; q++)
+          for (int r = 0; r < FR_RING; r++) CUDA_CHECK(cudaStreamSynchronize(ctx->sub_stream[q][r]));
+        sub_ev.inflight = false;
+        for (int r = 0; r < FR_RING; r++)
+          for (int q = 0; q < SUB_NCLS; q++) sub_ev.valid[r][q] = false;
+        Counters hq;
+        CUDA_CHECK(cudaMemcpyAsync(&hq, ws.cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        n_leaves = hq.n_leaves;
+        sub_nodes_used = (int64_t)hq.sub_nodes;
+      };
       while (F > 0) {
         S.levels++;
         pt.start();
-        ws.fr[cl ^ 1].ensure((size_t)F * 2, C, W, task == TASK_CLS, !replay);
-        for (int q = 0; q < NQ; q++) ws.q[cl ^ 1][q].ensure((size_t)F * 2, 1.5);
-        ws.pool.grow((size_t)(n_nodes + 2 * (int64_t)F), (size_t)n_nodes, (size_t)(n_leaves + F), (size_t)n_leaves, lw, st);
+        const int cn = (cl + 1) % FR_RING;
+        leaf_bound += (int64_t)F + sub_rows_level;
+        subnode_bound += 2 * sub_rows_level;
+        {
+          bool fits = ws.fr[cn].fits((size_t)F * 2, C, W, task == TASK_CLS, !replay) &&
+                      ws.pool.fits((size_t)(n_nodes + 2 * (int64_t)F), (size_t)leaf_bound, lw) &&
+                      ws.sub_nodes.cap >= (size_t)subnode_bound;
+          for (int q = 0; q < NQ; q++) fits = fits && ws.q[cn][q].cap >= (size_t)F * 2;
+          if (!fits) quiesce();
+        }
+        ws.fr[cn].ensure((size_t)F * 2, C, W, task == TASK_CLS, !replay);
+        for (int q = 0; q < NQ; q++) ws.q[cn][q].ensure((size_t)F * 2, 1.5);
+        ws.pool.grow((size_t)(n_nodes + 2 * (int64_t)F), (size_t)n_nodes, (size_t)leaf_bound, (size_t)n_leaves, lw, st);
+        if (subnode_bound > 0) ws.sub_nodes.grow_keep((size_t)subnode_bound, (size_t)sub_nodes_used, st);
         if (task != TASK_CLS && qn[Q_MID] + qn[Q_CTA] > 0)
           ws.scratch.ensure((size_t)NB * 2 * ((size_t)Bt * (size_t)n / 32 + (size_t)(qn[Q_MID] + qn[Q_CTA]) + 1) + 64, 1.0);
         pt.stop(0);
@@ -2768,20 +2943,21 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
         p.w_src = ws.ws[srcb].p;
         p.w_dst = ws.ws[srcb ^ 1].p;
         p.cur = ws.fr[cl].view();
-        p.nxt = ws.fr[cl ^ 1].view();
+        p.nxt = ws.fr[cn].view();
         for (int q = 0; q < NQ; q++) {
           p.q_cur[q] = ws.q[cl][q].p;
-          p.q_nxt[q] = ws.q[cl ^ 1][q].p;
+          p.q_nxt[q] = ws.q[cn][q].p;
         }
         p.o = ws.pool.view();
         p.scratch = ws.scratch.p;
+        p.sub_nodes = ws.sub_nodes.p;
         p.node_base_next = (int32_t)n_nodes;
         if (task == TASK_CLS)
-          launch_level<TASK_CLS>(ctx, p, qn, lc, pt, evt);
+          launch_level<TASK_CLS>(ctx, p, qn, lc, pt, evt, sub_ev, cl, cn);
         else if (task == TASK_CLSW)
-          launch_level<TASK_CLSW>(ctx, p, qn, lc, pt, evt);
+          launch_level<TASK_CLSW>(ctx, p, qn, lc, pt, evt, sub_ev, cl, cn);
         else
-          launch_level<TASK_REG>(ctx, p, qn, lc, pt, evt);
+          launch_level<TASK_REG>(ctx, p, qn, lc, pt, evt, sub_ev, cl, cn);
         pt.level_report((int)S.levels - 1, qn);
         pt.start();
         CUDA_CHECK(cudaMemcpyAsync(&hc, ws.cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
@@ -2793,15 +2969,25 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
         evt.drain(tacc);
         pt.stop(4);
         const int32_t nf = hc.next_f;
-        n_leaves = hc.n_leaves;
+        n_leaves = hc.n_leaves;  // (a snapshot while subtree kernels are in flight; exact again after quiesce())
         level_start.push_back((int32_t)n_nodes);
         n_nodes += nf;
         if (n_nodes > 0x7ffffff0) ET_FAIL(ET_EUNSUPPORTED, "batch exceeds 2^31 nodes; lower ETGPU_BATCH_TREES");
         for (int q = 0; q < NQ; q++) qn[q] = hc.q_count[q];
+        sub_rows_level = hc.sub_rows;
+        sub_nodes_used = (int64_t)hc.sub_nodes;
+        if (n_nodes + subnode_bound > 0x7ffffff0) ET_FAIL(ET_EUNSUPPORTED, "batch exceeds 2^31 nodes; lower ETGPU_BATCH_TREES");
         if (nf > 0) srcb ^= 1;
         F = nf;
-        cl ^= 1;
+        cl = cn;
       }
+      // the subtree kernels still in flight finish the batch
+      quiesce();
+      CUDA_CHECK(cudaMemcpyAsync(&hc, ws.cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      CUDA_CHECK(cudaGetLastError());
+      n_leaves = hc.n_leaves;
+      sub_nodes_used = (int64_t)hc.sub_nodes;
       S.v_mm += (int64_t)hc.st[ST_VMM];
       S.v_sc += (int64_t)hc.st[ST_VSC];
       S.s_rows += (int64_t)hc.st[ST_SROWS];
@@ -2812,7 +2998,6 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       S.replay_mismatches += (int64_t)hc.st[ST_MISMATCH];
       S.parallel_sum_nodes += (int64_t)hc.st[ST_PARNODES];
       S.ambiguous_splits += (int64_t)hc.st[ST_AMBIG];
-      S.nodes += n_nodes;
       // ---- creation order -> per-tree pre-order, on the device
       pt.start();
       ws.size.ensure((size_t)n_nodes);
@@ -2840,29 +3025,39 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
                                                                       ws.lpos.p);
         ctx->launches++;
       }
+      // (marker nodes of resident subtrees stand for whole blocks: the forest's node count comes from the offsets)
+      std::vector<int64_t> toff((size_t)Bt + 1);
+      CUDA_CHECK(cudaMemcpyAsync(toff.data(), ws.tree_off.p, ((size_t)Bt + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      const int64_t total_nodes = toff[(size_t)Bt] - node_base;
+      S.nodes += total_nodes;
       Seg sg;
-      sg.n_nodes = n_nodes;
+      sg.n_nodes = total_nodes;
       sg.n_leaves = n_leaves;
       sg.nodes = nullptr;
       sg.leaves = nullptr;
-      sg.nodes = static_cast<PNode *>(et_dev_alloc(ctx, (size_t)n_nodes * sizeof(PNode)));
+      sg.nodes = static_cast<PNode *>(et_dev_alloc(ctx, (size_t)total_nodes * sizeof(PNode)));
       sg.leaves = static_cast<double *>(et_dev_alloc(ctx, std::max<size_t>(1, (size_t)n_leaves * lw) * sizeof(double)));
       if (!sg.nodes || !sg.leaves) {
-        et_dev_free(ctx, sg.nodes, (size_t)n_nodes * sizeof(PNode));
+        et_dev_free(ctx, sg.nodes, (size_t)total_nodes * sizeof(PNode));
         et_dev_free(ctx, sg.leaves, std::max<size_t>(1, (size_t)n_leaves * lw) * sizeof(double));
-        ET_FAIL(ET_ENOMEM, "cannot allocate the forest (%lld nodes)", (long long)n_nodes);
+        ET_FAIL(ET_ENOMEM, "cannot allocate the forest (%lld nodes)", (long long)total_nodes);
       }
       segs.push_back(sg);
       k_scatter<<<(unsigned)ceil_div(n_nodes, 256), 256, 0, st>>>(po, (int32_t)n_nodes, lw, ws.pos.p, ws.lpos.p,
                                                                   ws.tree_off.p, ws.leaf_off.p, node_base, leaf_base,
                                                                   sg.nodes, sg.leaves);
       ctx->launches++;
-      std::vector<int64_t> toff((size_t)Bt + 1);
-      CUDA_CHECK(cudaMemcpyAsync(toff.data(), ws.tree_off.p, ((size_t)Bt + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      if (sub_nodes_used > 0) {
+        k_scatter_sub<<<(unsigned)ceil_div(n_nodes, 256), 256, 0, st>>>(po, (int32_t)n_nodes, lw, ws.pos.p, ws.lpos.p,
+                                                                        ws.tree_off.p, ws.leaf_off.p, node_base, leaf_base,
+                                                                        ws.sub_nodes.p, sg.nodes, sg.leaves);
+        ctx->launches++;
+      }
       CUDA_CHECK(cudaStreamSynchronize(st));
       CUDA_CHECK(cudaGetLastError());
       for (int32_t t = 0; t <= Bt; t++) out->tree_off[(size_t)(t0 + t)] = toff[(size_t)t];
-      node_base += n_nodes;
+      node_base += total_nodes;
       leaf_base += n_leaves;
       pt.stop(5);
     }
@@ -2909,6 +3104,8 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
     pt.report();
   } catch (...) {
     cudaStreamSynchronize(st);
+    for (int q = 0; q < SUB_NCLS; q++)
+      for (int r = 0; r < FR_RING; r++) cudaStreamSynchronize(ctx->sub_stream[q][r]);
     for (auto &sg : segs) {
       et_dev_free(ctx, sg.nodes, (size_t)sg.n_nodes * sizeof(PNode));
       et_dev_free(ctx, sg.leaves, std::max<size_t>(1, (size_t)sg.n_leaves * lw) * sizeof(double));

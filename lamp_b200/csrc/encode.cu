@@ -152,9 +152,77 @@ __global__ void __launch_bounds__(256) k_col_encode(const double *__restrict__ X
   *reinterpret_cast<uint32_t *>(codes + (int64_t)col * ldc + r0) = packed;
 }
 
+
+// Row-major copies for the resident subtree builder (subtree.cuh): 32 x 32 tiles through shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256) k_to_rowmajor(const T *__restrict__ src, int64_t ld_src, int64_t n, int32_t d,
+                                                     T *__restrict__ dst, int64_t ld_dst) {
+  __shared__ T tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int32_t c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int32_t c = c0 + j;
+    const int64_t r = r0 + threadIdx.x;
+    if (r < n && c < d) tile[j][threadIdx.x] = src[(int64_t)c * ld_src + r];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int64_t r = r0 + j;
+    const int32_t c = c0 + threadIdx.x;
+    if (r < n && c < d) dst[r * ld_dst + c] = tile[threadIdx.x][j];
+  }
+}
+
+}  // namespace
+
+void et_data_drop_rowmajor(et_data *D) {
+  et_dev_free(D->ctx, D->r8, D->r8_bytes);
+  et_dev_free(D->ctx, D->xr, D->xr_bytes);
+  D->r8 = nullptr;
+  D->xr = nullptr;
+  D->r8_bytes = D->xr_bytes = 0;
+}
+
+// Builds the row-major copy the resident subtree builder stages rows from (byte codes if the table is coded,
+// else FP64).  A failed allocation just leaves the copy absent: the builder then keeps gathering.
+void et_data_rowmajor(et_ctx *ctx, et_data *D) {
+  if (D->n <= 0 || D->d <= 0 || D->coded == 0) return;
+  const char *env = getenv("ETGPU_SUB_NCLS");  // the subtree builder is opt-in (build.cu)
+  if (!env || atoi(env) <= 0) return;
+  cudaStream_t st = ctx->stream;
+  dim3 block(32, 8), grid((unsigned)ceil_div(D->n, 32), (unsigned)ceil_div(D->d, 32));
+  if (D->coded == 1 && !D->r8) {
+    D->rs8 = ((int64_t)D->d + 15) / 16 * 16;
+    D->r8_bytes = (size_t)D->n * (size_t)D->rs8;
+    D->r8 = static_cast<uint8_t *>(et_dev_alloc(ctx, D->r8_bytes));
+    if (!D->r8) {
+      D->r8_bytes = 0;
+      cudaGetLastError();
+      return;
+    }
+    cudaMemsetAsync(D->r8, 0, D->r8_bytes, st);
+    k_to_rowmajor<uint8_t><<<grid, block, 0, st>>>(D->c8, D->ldc, D->n, D->d, D->r8, D->rs8);
+    ctx->launches++;
+  } else if (D->coded == -1 && !D->xr) {
+    D->rsd = ((int64_t)D->d + 1) / 2 * 2;
+    D->xr_bytes = (size_t)D->n * (size_t)D->rsd * sizeof(double);
+    D->xr = static_cast<double *>(et_dev_alloc(ctx, D->xr_bytes));
+    if (!D->xr) {
+      D->xr_bytes = 0;
+      cudaGetLastError();
+      return;
+    }
+    cudaMemsetAsync(D->xr, 0, D->xr_bytes, st);
+    k_to_rowmajor<double><<<grid, block, 0, st>>>(D->x, D->ld, D->n, D->d, D->xr, D->rsd);
+    ctx->launches++;
+  }
+}
+
+namespace {
 }  // namespace
 
 void et_data_drop_codes(et_data *D) {
+  et_data_drop_rowmajor(D);
   et_dev_free(D->ctx, D->c8, (size_t)D->d * (size_t)D->ldc);
   et_dev_free(D->ctx, D->dict, (size_t)D->d * 256 * sizeof(double));
   et_dev_free(D->ctx, D->coff, (size_t)D->d);
@@ -170,6 +238,7 @@ void et_data_encode(et_ctx *ctx, et_data *D) {
   const char *env = getenv("ETGPU_NO_CODES");
   if ((env && atoi(env) != 0) || D->n <= 0 || D->d <= 0) {
     D->coded = -1;
+    et_data_rowmajor(ctx, D);
     return;
   }
   cudaStream_t st = ctx->stream;
@@ -202,7 +271,9 @@ void et_data_encode(et_ctx *ctx, et_data *D) {
   if (!ok) {
     et_data_drop_codes(D);
     D->coded = -1;
+    et_data_rowmajor(ctx, D);
     return;
   }
   D->coded = 1;
+  et_data_rowmajor(ctx, D);
 }

@@ -21,8 +21,13 @@ struct et_ctx {
   };
   std::vector<Block> cache;
   size_t cache_bytes = 0;
-  cudaStream_t side[7] = {};
-  cudaEvent_t ev_fork = nullptr, ev_join[7] = {};
+  static constexpr int N_SIDE = 12;
+  cudaStream_t side[N_SIDE] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[N_SIDE] = {};
+  // resident-subtree kernels: one low-priority stream per (team class, frontier ring slot), so the kernels of
+  // successive levels overlap instead of queueing behind each other's longest subtree
+  static constexpr int N_SUB_CLS = 5, N_SUB_RING = 4;
+  cudaStream_t sub_stream[N_SUB_CLS][N_SUB_RING] = {};
 };
 void et_workspace_free(Workspace *ws);
 // api.cu: device blocks through the context's cache (null on failure, like cudaMalloc != cudaSuccess)
@@ -42,6 +47,13 @@ struct et_data {
   uint8_t *coff = nullptr; // [d] 0 if the column holds a NaN, else 1
   int64_t ldc = 0;         // code column stride in bytes (n rounded up to 128)
   double *dict = nullptr;  // [d][256] ascending distinct values, padded with +inf
+  // row-major copies for the resident subtree builder (subtree.cuh): byte codes [n][rs8] when the table is coded,
+  // else FP64 [n][rsd]; rows are 16-byte multiples so a row moves with full vector loads
+  uint8_t *r8 = nullptr;
+  int64_t rs8 = 0;   // bytes per coded row
+  double *xr = nullptr;
+  int64_t rsd = 0;   // doubles per FP64 row
+  size_t r8_bytes = 0, xr_bytes = 0;
   // attached targets / weights (resident)
   int32_t *y_cls = nullptr;
   int32_t num_classes = 0;
@@ -93,6 +105,8 @@ struct BuildArgs {
 // encode.cu
 void et_data_encode(et_ctx *ctx, et_data *data);
 void et_data_drop_codes(et_data *data);  // gives the coded copy back to the context's block cache
+void et_data_rowmajor(et_ctx *ctx, et_data *data);  // row-major copy for the resident subtree builder
+void et_data_drop_rowmajor(et_data *data);
 // build.cu
 void et_build_forest(et_ctx *ctx, et_data *data, const BuildArgs &a, et_forest *out, et_stats *stats);
 // predict.cu

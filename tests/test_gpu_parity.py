@@ -14,11 +14,14 @@ pytestmark = pytest.mark.gpu
 NAN = float("nan")
 
 
-@pytest.fixture(autouse=True, params=["codes", "fp64"])
+@pytest.fixture(autouse=True, params=["codes", "fp64", "codes-subtrees", "fp64-subtrees"])
 def table_coding(request, monkeypatch):
-    """Every test runs twice: with the byte-coded copy of the table (encode.cu; used whenever all columns
-    have <= 255 distinct values) and with FP64 gathers only (ETGPU_NO_CODES=1)."""
-    monkeypatch.setenv("ETGPU_NO_CODES", "1" if request.param == "fp64" else "0")
+    """Every test runs with the byte-coded copy of the table (encode.cu; used whenever all columns have <= 255
+    distinct values) and with FP64 gathers only (ETGPU_NO_CODES=1), each with the level-wise kernels alone and
+    with the opt-in resident subtree builder (subtree.cuh, ETGPU_SUB_NCLS=5: nodes of up to ~200 rows are built
+    to the leaves out of shared memory, asynchronously to the level loop)."""
+    monkeypatch.setenv("ETGPU_NO_CODES", "1" if request.param.startswith("fp64") else "0")
+    monkeypatch.setenv("ETGPU_SUB_NCLS", "5" if request.param.endswith("subtrees") else "0")
     return request.param
 
 
