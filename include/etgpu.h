@@ -63,6 +63,14 @@ int et_data_dense_colblock(et_ctx *ctx, et_data *data, const double *cols_host, 
 /* Same, from a device-resident row-major matrix (no host copy; used to keep inputs in HBM). */
 int et_data_dense_rowmajor_device(et_ctx *ctx, const double *x_dev, int64_t n, int32_t d,
                                   et_data **out);
+/* Sparse input in compressed-sparse-column form (BASELINE.json configs[3]): column c holds the entries
+ * colptr[c] .. colptr[c+1]-1 of (rowidx, val); entries not listed are 0.0 with DENSE semantics (the reference
+ * has no sparse Mat: a CSC table builds exactly the forest of its dense expansion, pkg:931-941).  The table is
+ * expanded on the device into the resident column-major matrix (and byte-coded like any other table when every
+ * column has <= 255 distinct values); row indices must lie in [0, n), colptr must be non-decreasing with
+ * colptr[0] == 0, else ET_EINVAL.  A row listed twice in one column keeps the later entry. */
+int et_data_csc(et_ctx *ctx, const int64_t *colptr_host, const int32_t *rowidx_host, const double *val_host,
+                int64_t n, int32_t d, et_data **out);
 /* Attach targets / sample weights that stay resident in HBM across builds.  n_target must equal
  * the table's rows (the reference's require at pkg:624-627 / 715-718) else ET_EINVAL.  Weights must
  * be non-negative (pkg:631-633); pass NULL to clear (sampleWeights = None). */

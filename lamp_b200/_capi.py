@@ -52,6 +52,7 @@ SIGNATURES = {
     "et_data_dense_alloc": (C.c_int, [vp, C.c_int64, C.c_int32, C.POINTER(vp)]),
     "et_data_dense_colblock": (C.c_int, [vp, vp, dp, C.c_int32, C.c_int32]),
     "et_data_dense_rowmajor_device": (C.c_int, [vp, vp, C.c_int64, C.c_int32, C.POINTER(vp)]),
+    "et_data_csc": (C.c_int, [vp, C.POINTER(C.c_int64), ip, dp, C.c_int64, C.c_int32, C.POINTER(vp)]),
     "et_data_set_target_classification": (C.c_int, [vp, vp, ip, C.c_int64, C.c_int32]),
     "et_data_set_target_regression": (C.c_int, [vp, vp, dp, C.c_int64]),
     "et_data_set_weights": (C.c_int, [vp, vp, dp, C.c_int64]),

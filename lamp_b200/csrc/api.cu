@@ -290,6 +290,80 @@ extern "C" int et_data_dense_rowmajor_device(et_ctx *ctx, const double *x_dev, i
   ET_API_END
 }
 
+// one thread per stored entry of a block of columns: x[col][row] = val (the table was zero-filled before)
+__global__ void k_csc_scatter(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                              const double *__restrict__ val, int32_t c0, int32_t ncols, int64_t e0, int64_t ne,
+                              double *__restrict__ x, int64_t ld) {
+  const int64_t e = e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= e0 + ne) return;
+  int lo = 0, hi = ncols;  // the column of entry e: last c with colptr[c0 + c] <= e
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (colptr[c0 + mid] <= e)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  x[(int64_t)(c0 + lo) * ld + rowidx[e - e0]] = val[e - e0];
+}
+
+extern "C" int et_data_csc(et_ctx *ctx, const int64_t *colptr, const int32_t *rowidx, const double *val, int64_t n,
+                           int32_t d, et_data **out) {
+  ET_API_BEGIN
+  if (!ctx || !out || !colptr) ET_FAIL(ET_EINVAL, "et_data_csc: NULL argument");
+  if (n < 0 || d < 0) ET_FAIL(ET_EINVAL, "negative table dimensions");
+  if (colptr[0] != 0) ET_FAIL(ET_EINVAL, "et_data_csc: colptr[0] must be 0");
+  for (int32_t c = 0; c < d; c++)
+    if (colptr[c + 1] < colptr[c]) ET_FAIL(ET_EINVAL, "et_data_csc: colptr decreases at column %d", c);
+  const int64_t nnz = colptr[d];
+  if (nnz > 0 && (!rowidx || !val)) ET_FAIL(ET_EINVAL, "et_data_csc: NULL argument");
+  for (int64_t e = 0; e < nnz; e++)
+    if (rowidx[e] < 0 || rowidx[e] >= n) ET_FAIL(ET_EINVAL, "et_data_csc: row index %d outside [0,%lld)", rowidx[e], (long long)n);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  et_data *D = data_alloc(ctx, n, d);
+  int64_t *d_colptr = nullptr;
+  int32_t *d_row = nullptr;
+  double *d_val = nullptr;
+  const int64_t chunk_max = (int64_t)16 << 20;  // stored entries per upload (192 MB of staging)
+  try {
+    CUDA_CHECK(cudaMemsetAsync(D->x, 0, D->x_bytes, ctx->stream));
+    if (nnz > 0 && n > 0) {
+      CUDA_CHECK(cudaMalloc((void **)&d_colptr, ((size_t)d + 1) * sizeof(int64_t)));
+      CUDA_CHECK(cudaMemcpyAsync(d_colptr, colptr, ((size_t)d + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+      const int64_t cap = std::min(nnz, chunk_max);
+      CUDA_CHECK(cudaMalloc((void **)&d_row, (size_t)cap * sizeof(int32_t)));
+      CUDA_CHECK(cudaMalloc((void **)&d_val, (size_t)cap * sizeof(double)));
+      for (int64_t e0 = 0; e0 < nnz; e0 += cap) {
+        const int64_t ne = std::min(cap, nnz - e0);
+        // the columns this run of entries touches
+        const int32_t c0 = (int32_t)(std::upper_bound(colptr, colptr + d + 1, e0) - colptr) - 1;
+        const int32_t c1 = (int32_t)(std::upper_bound(colptr, colptr + d + 1, e0 + ne - 1) - colptr) - 1;
+        CUDA_CHECK(cudaMemcpyAsync(d_row, rowidx + e0, (size_t)ne * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(d_val, val + e0, (size_t)ne * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        k_csc_scatter<<<(unsigned)ceil_div(ne, 256), 256, 0, ctx->stream>>>(d_colptr, d_row, d_val, c0, c1 - c0 + 1, e0, ne,
+                                                                        D->x, D->ld);
+        ctx->launches++;
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // (the staging buffers are reused)
+      }
+    }
+    et_data_encode(ctx, D);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(cudaGetLastError());
+  } catch (...) {
+    cudaFree(d_colptr);
+    cudaFree(d_row);
+    cudaFree(d_val);
+    et_data_free(D);
+    throw;
+  }
+  cudaFree(d_colptr);
+  cudaFree(d_row);
+  cudaFree(d_val);
+  *out = D;
+  ET_API_END
+}
+
 template <typename T>
 static void upload_vec(et_ctx *ctx, T **dst, const T *src, int64_t n) {
   if (*dst) {

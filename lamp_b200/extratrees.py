@@ -203,6 +203,21 @@ class DeviceData:
             check(capi.lib().et_data_dense_colblock(ctx.h, h, ptr(blk, dp), first, blk.shape[0]))
         return out
 
+    @staticmethod
+    def from_csc(colptr, rowidx, values, n: int, d: int, ctx: Optional[Context] = None) -> "DeviceData":
+        """Compressed-sparse-column input (entries not listed are 0.0, dense semantics).  Also accepts the
+        attributes of a scipy.sparse.csc_matrix: from_csc(m.indptr, m.indices, m.data, *m.shape)."""
+        ctx = ctx or default_context()
+        cp = np.ascontiguousarray(colptr, dtype=np.int64)
+        ri = np.ascontiguousarray(rowidx, dtype=np.int32)
+        va = np.ascontiguousarray(values, dtype=np.float64)
+        if len(cp) != d + 1 or len(ri) != len(va) or (len(cp) and cp[-1] != len(va)):
+            raise ValueError("from_csc: colptr must have d + 1 entries ending at the number of stored values")
+        h = C.c_void_p()
+        check(capi.lib().et_data_csc(ctx.h, cp.ctypes.data_as(C.POINTER(C.c_int64)), ptr(ri, ip), ptr(va, dp), n, d,
+                                     C.byref(h)))
+        return DeviceData(ctx, h)
+
     @property
     def shape(self):
         n, d = C.c_int64(), C.c_int32()

@@ -275,6 +275,56 @@ def test_replay_coding_edge_cases(with_nan):
     assert_trees_bit_exact(gf, of)
 
 
+# ---- CSC input (BASELINE.json configs[3], down-scaled): dense semantics ----------------------------------------
+def _sparse_table(n, d, density, seed):
+    """per column Binomial(n, density) rows, values abs(N(0,1)) + 0.1"""
+    rng = np.random.default_rng(seed)
+    colptr, rows, vals = [0], [], []
+    for _ in range(d):
+        r = np.flatnonzero(rng.random(n) < density).astype(np.int32)
+        rows.append(r)
+        vals.append(np.abs(rng.normal(size=len(r))) + 0.1)
+        colptr.append(colptr[-1] + len(r))
+    return np.array(colptr, np.int64), np.concatenate(rows), np.concatenate(vals)
+
+
+def test_csc_input_builds_the_forest_of_its_dense_expansion():
+    n, d = 20000, 500
+    colptr, rowidx, vals = _sparse_table(n, d, 0.01, 4)
+    dense = np.zeros((n, d))
+    for c in range(d):
+        dense[rowidx[colptr[c]:colptr[c + 1]], c] = vals[colptr[c]:colptr[c + 1]]
+    rng = np.random.default_rng(5)
+    y = ((dense[:, :50].sum(axis=1) + 0.2 * rng.normal(size=n)) > np.median(dense[:, :50].sum(axis=1))).astype(np.int32)
+    of = O.build_forest_classification(dense, y, None, 2, 2, 100, 2, 2, seed=4, record_trace=True)
+    dd = et.DeviceData.from_csc(colptr, rowidx, vals, n, d)
+    assert dd.shape == (n, d)
+    dd.set_target_classification(y, 2)
+    gf = et.buildForestClassification(dd, None, None, 2, 2, 100, 2, 2, seed=4, replay=oracle_replay(of))
+    assert_trees_bit_exact(gf, of)
+    assert np.array_equal(et.predictClassification(gf, dense[:3000]), of.predict(dense[:3000]))
+    # free-running: the CSC table and its dense expansion give the same forest
+    f1 = et.buildForestClassification(dd, None, None, 2, 2, 100, 3, 2, seed=9)
+    f2 = et.buildForestClassification(dense, y, None, 2, 2, 100, 3, 2, seed=9)
+    a, b = f1.export_packed(), f2.export_packed()
+    for field in ("feat", "right_or_leaf"):
+        assert np.array_equal(a["nodes"][field], b["nodes"][field])
+    assert np.array_equal(a["nodes"]["cut"].view(np.int64), b["nodes"]["cut"].view(np.int64))  # (leaves hold NaN)
+    assert np.array_equal(a["leaves"], b["leaves"])
+    dd.free()
+
+
+def test_csc_input_argument_errors():
+    with pytest.raises(ValueError):  # row index outside the table
+        et.DeviceData.from_csc([0, 1], [7], [1.0], 5, 1)
+    with pytest.raises(ValueError):  # colptr decreases
+        et.DeviceData.from_csc([0, 2, 1], [0, 1], [1.0, 2.0], 5, 2)
+    empty = et.DeviceData.from_csc([0, 0, 0], [], [], 6, 2)  # an all-zero table is legal
+    empty.set_target_classification(np.array([0, 1, 0, 1, 0, 1], np.int32), 2)
+    f = et.buildForestClassification(empty, None, None, 2, 2, 2, 3, 1, seed=1)
+    assert all(isinstance(t, et.ClassificationLeaf) for t in f)  # every feature is constant: roots are leaves
+
+
 # ---- BASELINE.json sizes: size-independent properties --------------------------------------------------------
 def test_full_size_mnist_shaped_properties(table_coding):
     """configs[1] at full size (60000 x 784, 10 classes; the bench generator): every fully grown tree (nMin=2)
