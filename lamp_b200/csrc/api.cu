@@ -463,7 +463,6 @@ static void check_build_common(et_ctx *ctx, et_data *D, int32_t k, int32_t m, in
   if (!ctx || !D || !out) ET_FAIL(ET_EINVAL, "build: NULL argument");
   if (D->ctx != ctx) ET_FAIL(ET_EINVAL, "build: data belongs to another context");
   if (m < 0) ET_FAIL(ET_EINVAL, "build: m must be >= 0");
-  if (best_split) ET_FAIL(ET_EUNSUPPORTED, "bestSplit=true (pkg:56-202, 298-426) is not implemented on the GPU yet");
   (void)k;
 }
 

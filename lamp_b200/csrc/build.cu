@@ -2457,6 +2457,8 @@ struct EventTimer {
   }
 };
 
+#include "best.cuh"
+
 struct LevelCfg {
   bool coded;      // nodes of up to 512 samples: k_lane on byte codes
   bool coded_big;  // larger nodes: byte-coded CTA teams (unweighted classification, <= 32 classes)
@@ -2691,7 +2693,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
   }
   if (!lc.coded) lc.smem_lane[0] = (size_t)lane_smem_bytes(task, C, W, replay, 1, 8);
   // resident subtrees: how many rows of the row-major copy fit one SM next to the teams' scratch
-  {
+  if (!a.best_split) {
     const bool have_rm = lc.coded ? (D->r8 != nullptr) : (D->xr != nullptr);
     const int64_t rowbytes = lc.coded ? D->rs8 : D->rsd * 8;
     int smem_max = 0;
@@ -2736,6 +2738,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
   CUDA_CHECK(cudaEventCreate(&ev0));
   CUDA_CHECK(cudaEventCreate(&ev1));
   SubEvents sub_ev;
+  BestBufs best_bufs;  // (bestSplit builds only)
   for (int r = 0; r < FR_RING; r++)
     for (int q = 0; q < SUB_NCLS; q++) CUDA_CHECK(cudaEventCreateWithFlags(&sub_ev.ev[r][q], cudaEventDisableTiming));
   CUDA_CHECK(cudaEventRecord(ev0, st));
@@ -2857,6 +2860,8 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       for (int q = 1; q < 4; q++) p.cls_max[Q_LANE0 + q] = lc.coded ? (NT_MAX << q) : NT_MAX;
       p.cls_max[Q_WARP] = NW_MAX;
       p.cls_max[Q_MID] = NM_MAX;
+      if (a.best_split)  // bestSplit: one kernel family (best.cuh), every node in the last queue
+        for (int q = 0; q < NQ - 1; q++) p.cls_max[q] = 0;
       p.R8 = D->r8;
       p.XR = D->xr;
       p.sub_ncls = lc.sub_ncls;
@@ -2952,7 +2957,16 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
         p.scratch = ws.scratch.p;
         p.sub_nodes = ws.sub_nodes.p;
         p.node_base_next = (int32_t)n_nodes;
-        if (task == TASK_CLS)
+        if (a.best_split) {
+          const int e0 = evt.rec(st);
+          if (task == TASK_CLS)
+            launch_level_best<TASK_CLS>(ctx, p, qn[Q_CTA], best_bufs, (int64_t)ns);
+          else if (task == TASK_CLSW)
+            launch_level_best<TASK_CLSW>(ctx, p, qn[Q_CTA], best_bufs, (int64_t)ns);
+          else
+            launch_level_best<TASK_REG>(ctx, p, qn[Q_CTA], best_bufs, (int64_t)ns);
+          evt.spans[0].push_back({e0, evt.rec(st)});
+        } else if (task == TASK_CLS)
           launch_level<TASK_CLS>(ctx, p, qn, lc, pt, evt, sub_ev, cl, cn);
         else if (task == TASK_CLSW)
           launch_level<TASK_CLSW>(ctx, p, qn, lc, pt, evt, sub_ev, cl, cn);

@@ -275,6 +275,53 @@ def test_replay_coding_edge_cases(with_nan):
     assert_trees_bit_exact(gf, of)
 
 
+# ---- bestSplit = true (pkg:56-202, 298-426): every sample value tried as the cutpoint ------------------------------
+@pytest.mark.parametrize("rows,k,max_depth", [(600, 28, 4), (1500, 5, 200)])
+def test_replay_best_split_classification(mnist, rows, k, max_depth):
+    x, y = mnist
+    x, y = x[:rows], y[:rows]
+    of = O.build_forest_classification(x, y, None, 10, 2, k, 2, 2, best_split=True, max_depth=max_depth, seed=6,
+                                       record_trace=True)
+    gf = et.buildForestClassification(x, y, None, 10, 2, k, 2, 2, bestSplit=True, maxDepth=max_depth, seed=6,
+                                      replay=oracle_replay(of))
+    assert gf.stats["replay_mismatches"] == 0
+    assert_trees_bit_exact(gf, of)
+    so, sg = of.stats(), gf.stats
+    for key in ("v_mm", "v_sc", "s_rows", "p_rows", "draws", "const_hits", "scored", "nodes"):
+        assert so[key] == sg[key], (key, so[key], sg[key])
+
+
+def test_replay_best_split_weighted_and_missing():
+    x, y = synth_classification(700, 9, 4, 21, nan_frac=0.05, const_cols=1, quantize=4)
+    w = np.random.default_rng(3).uniform(0.0, 2.0, size=len(y))
+    w[::7] = 0.0
+    of = O.build_forest_classification(x, y, w, 4, 2, 3, 3, 2, best_split=True, seed=8, record_trace=True)
+    gf = et.buildForestClassification(x, y, w, 4, 2, 3, 3, 2, bestSplit=True, seed=8, replay=oracle_replay(of))
+    assert gf.stats["replay_mismatches"] == 0
+    assert_trees_bit_exact(gf, of)
+    assert np.array_equal(et.predictClassification(gf, x), of.predict(x))
+
+
+@pytest.mark.parametrize("nan_frac", [0.0, 0.04])
+def test_replay_best_split_regression(nan_frac):
+    x, y = synth_regression(800, 8, 13, nan_frac=nan_frac)
+    of = O.build_forest_regression(x, y, 3, 3, 2, 2, best_split=True, max_depth=12, seed=4, record_trace=True)
+    gf = et.buildForestRegression(x, y, 3, 3, 2, 2, bestSplit=True, maxDepth=12, seed=4, replay=oracle_replay(of))
+    assert gf.stats["replay_mismatches"] == 0
+    assert_trees_bit_exact(gf, of)
+    assert np.array_equal(et.predictRegression(gf, x), of.predict(x))
+
+
+def test_free_best_split_mnist(mnist):  # tst:320-356 and tst:478-513
+    x, y = mnist
+    f = et.buildForestClassification(x, y, None, 10, 2, 32, 1, 1, bestSplit=True, maxDepth=1, seed=1)
+    assert (et.predictClassification(f, x).argmax(1) == y).mean() > 0.15
+    t = f[0]
+    assert isinstance(t, et.ClassificationNonLeaf) and isinstance(t.left, et.ClassificationLeaf)
+    fr = et.buildForestRegression(x[:3000], y[:3000].astype(np.float64), 2, 32, 1, 8, bestSplit=True, maxDepth=3, seed=2)
+    assert (np.round(et.predictRegression(fr, x[:3000])).astype(np.int64) == y[:3000]).mean() > 0.15
+
+
 # ---- CSC input (BASELINE.json configs[3], down-scaled): dense semantics ----------------------------------------
 def _sparse_table(n, d, density, seed):
     """per column Binomial(n, density) rows, values abs(N(0,1)) + 0.1"""
