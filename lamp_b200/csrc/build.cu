@@ -193,7 +193,8 @@ struct P {
   int32_t c8_small;    // the coded table is smaller than 4 GiB: gathers use 32-bit offsets from C8
   int32_t cls_max[NQ - 1];
   // resident subtree builder (subtree.cuh)
-  const uint8_t *R8;   // row-major byte codes [n][sub_rowbytes]
+  const uint8_t *R8;   // row-major byte codes [n][r8_stride] (also gathered by k_lane)
+  int32_t r8_stride;
   const double *XR;    // row-major FP64 [n][sub_rowbytes / 8]
   int32_t sub_ncls;    // size classes 0 .. sub_ncls - 1 are built by k_sub (0: off)
   int32_t sub_rw, sub_rowbytes;  // staged rows per warp, bytes per staged row
@@ -1969,15 +1970,24 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? 6 : 4) k_lane(P p, in
       // byte codes are parked four positions to a word, [position / 4][lane][position % 4]: pass 2 reads one word
       // per four samples.  The gather address is a 32-bit offset from the table base (host-checked: the coded
       // table is smaller than 4 GiB, else the 64-bit form is used).
-      const uint8_t *c8base = CODED ? p.C8 : nullptr;
-      const uint32_t coloff32 = (CODED && p.c8_small) ? (uint32_t)((int64_t)(act0 ? f : 0) * p.ldc) : 0u;
+      // Byte codes are gathered from the ROW-major copy when it exists: the 32 lanes of a gather read 32 features of
+      // ONE row, i.e. 32 bytes inside one 784-byte row (<= 7 cache lines, ~18 sectors) instead of 32 sectors in 32
+      // different columns (32 lines).  These nodes sit deep in the tree, where a column-major gather gets no
+      // sector reuse between the rows of a node either.
+      const bool rowmajor = CODED && p.R8 != nullptr;
+      const uint8_t *c8base = CODED ? (rowmajor ? p.R8 : p.C8) : nullptr;
+      const uint32_t rstride = rowmajor ? (uint32_t)p.r8_stride : 1u;
+      const uint32_t coloff32 = (CODED && p.c8_small)
+                                    ? (rowmajor ? (uint32_t)(act0 ? f : 0) : (uint32_t)((int64_t)(act0 ? f : 0) * p.ldc))
+                                    : 0u;
+      if (rowmajor) col = reinterpret_cast<const VT *>(p.R8) + (act0 ? f : 0);
       uint8_t *s_xb = reinterpret_cast<uint8_t *>(s_x);
       // (inactive lanes gather from column 0: no predicate, no branch, so all gathers of a chunk stay in flight)
       auto visit = [&](auto small_tab, int32_t rj, int pos) {
         if (CODED) {
           const uint32_t b8 = decltype(small_tab)::value
-                                  ? (uint32_t)__ldg(c8base + (coloff32 + (uint32_t)rj))
-                                  : (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(col) + rj);
+                                  ? (uint32_t)__ldg(c8base + (coloff32 + (uint32_t)rj * rstride))
+                                  : (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(col) + (int64_t)rj * rstride);
           s_xb[(((pos >> 2) * 32 + lane) << 2) + (pos & 3)] = (uint8_t)b8;
           mxb = max(mxb, b8);
           mnt = min(mnt, b8 - K);
@@ -2466,6 +2476,7 @@ struct LevelCfg {
   size_t smem_lane[5];                   // k_lane per warp, classes 0..4
   int sub_ncls = 0;                      // classes 0 .. sub_ncls - 1: resident subtrees (k_sub), team width 1 << class
   int sub_rw = 0, sub_rowbytes = 0;
+  int sub_from = 0;                      // first level whose nodes may be handed to k_sub
   size_t smem_sub[SUB_NCLS] = {0};       // k_sub per CTA
 };
 
@@ -2627,9 +2638,9 @@ void set_smem_attr(const LevelCfg &lc) {
   }
   if (lc.coded) {
     CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(lc.smem_lane[1] * LANE_WARPS)));
+                                    (int)(std::max(lc.smem_lane[0], lc.smem_lane[1]) * LANE_WARPS)));
     CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(lc.smem_lane[4] * LANE_WARPS)));
+                                    (int)(std::max(lc.smem_lane[2], std::max(lc.smem_lane[3], lc.smem_lane[4])) * LANE_WARPS)));
   } else {
     CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(lc.smem_lane[0] * LANE_WARPS)));
@@ -2704,6 +2715,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
     int ncls = 0, rw_cap = 16;
     if (const char *env = getenv("ETGPU_SUB_NCLS")) ncls = std::max(0, std::min(SUB_NCLS, atoi(env)));
     if (const char *env = getenv("ETGPU_SUB_RW")) rw_cap = std::max(1, std::min(16, atoi(env)));
+    if (const char *env = getenv("ETGPU_SUB_FROM_LEVEL")) lc.sub_from = std::max(0, atoi(env));
     if (have_rm && ncls > 0 && (task == TASK_REG || C <= 256) && rowbytes < (1 << 20)) {
       int rw = rw_cap;
       // a team of 1 << q warps is one CTA; SUB_WARPS >> q of them share an SM (1 KB per CTA is reserved)
@@ -2854,8 +2866,11 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       p.ldc = D->ldc;
       p.dict = D->dict;
       p.coff = D->coff;
-      p.c8_small = ((uint64_t)D->ldc * (uint64_t)d < ((uint64_t)1 << 32)) ? 1 : 0;
-      for (int q = 0; q < Q_LANE0; q++) p.cls_max[q] = (q < lc.sub_ncls) ? (lc.sub_rw << q) : 0;  // 0: empty class
+      p.c8_small = ((uint64_t)D->ldc * (uint64_t)d < ((uint64_t)1 << 32) &&
+                    (uint64_t)std::max<int64_t>(D->rs8, 1) * (uint64_t)n < ((uint64_t)1 << 32))
+                       ? 1
+                       : 0;
+      for (int q = 0; q < Q_LANE0; q++) p.cls_max[q] = 0;  // 0: empty class (set per level below)
       p.cls_max[Q_LANE0] = NT_MAX;
       for (int q = 1; q < 4; q++) p.cls_max[Q_LANE0 + q] = lc.coded ? (NT_MAX << q) : NT_MAX;
       p.cls_max[Q_WARP] = NW_MAX;
@@ -2863,13 +2878,19 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       if (a.best_split)  // bestSplit: one kernel family (best.cuh), every node in the last queue
         for (int q = 0; q < NQ - 1; q++) p.cls_max[q] = 0;
       p.R8 = D->r8;
+      p.r8_stride = (int32_t)D->rs8;
       p.XR = D->xr;
-      p.sub_ncls = lc.sub_ncls;
+      p.sub_ncls = 0;
+      if (lc.sub_ncls > 0 && lc.sub_from <= 0) {  // the roots themselves may be small enough
+        p.sub_ncls = lc.sub_ncls;
+        for (int q = 0; q < lc.sub_ncls; q++) p.cls_max[q] = lc.sub_rw << q;
+      }
       p.sub_rw = lc.sub_rw;
       p.sub_rowbytes = lc.sub_rowbytes;
       p.tr = Trace{d_tr_cand_begin, d_tr_cand_count, d_tr_left, d_tr_right, d_tr_cand_feature, d_tr_cand_u,
                    d_tr_cand_flag};
       int srcb = 0, cl = 0;  // cl: frontier slot of the current level (ring of FR_RING)
+      const int level0 = (int)S.levels;  // levels counted before this batch
       int32_t F = Bt;
       ws.fr[0].ensure((size_t)F, C, W, task == TASK_CLS, !replay);
       for (int q = 0; q < NQ; q++) ws.q[0][q].ensure((size_t)F, 1.5);
@@ -2899,7 +2920,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       std::vector<int32_t> level_start{0};
       int32_t qn[NQ] = {0};
       qn[size_class(p, n)] = Bt;
-      int64_t sub_rows_level = (size_class(p, n) < lc.sub_ncls) ? (int64_t)Bt * n : 0;  // rows entering k_sub this level
+      int64_t sub_rows_level = (size_class(p, n) < p.sub_ncls) ? (int64_t)Bt * n : 0;  // rows entering k_sub this level
       int64_t sub_nodes_used = 0;
       int64_t leaf_bound = 0, subnode_bound = 0;  // upper bounds of the leaves / block nodes allocated so far
       Counters hc;
@@ -2957,6 +2978,13 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
         p.scratch = ws.scratch.p;
         p.sub_nodes = ws.sub_nodes.p;
         p.node_base_next = (int32_t)n_nodes;
+        // the children made at this level go to the subtree classes once the level loop has reached sub_from
+        // (the wide top levels stay with the gathering kernels; the long thin tail of the tree is where a
+        // resident subtree saves a kernel launch and a host round trip per level)
+        if (lc.sub_ncls > 0 && (int)S.levels - 1 - level0 + 1 >= lc.sub_from) {
+          p.sub_ncls = lc.sub_ncls;
+          for (int q = 0; q < lc.sub_ncls; q++) p.cls_max[q] = lc.sub_rw << q;
+        }
         if (a.best_split) {
           const int e0 = evt.rec(st);
           if (task == TASK_CLS)
@@ -2980,7 +3008,16 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
         CUDA_CHECK(cudaMemsetAsync(&ws.cnt.p->scratch_words, 0, sizeof(unsigned long long), st));
         CUDA_CHECK(cudaStreamSynchronize(st));
         CUDA_CHECK(cudaGetLastError());
-        evt.drain(tacc);
+        {
+          const double before = tacc[0];
+          evt.drain(tacc);
+          static const bool level_ms = getenv("ETGPU_LEVEL_MS") != nullptr;
+          if (level_ms) {
+            fprintf(stderr, "[etgpu level %3d] %.3f ms | nodes", (int)S.levels - 1, tacc[0] - before);
+            for (int q = 0; q < NQ; q++) fprintf(stderr, " %d", qn[q]);
+            fprintf(stderr, "\n");
+          }
+        }
         pt.stop(4);
         const int32_t nf = hc.next_f;
         n_leaves = hc.n_leaves;  // (a snapshot while subtree kernels are in flight; exact again after quiesce())

@@ -187,8 +187,13 @@ void et_data_drop_rowmajor(et_data *D) {
 // else FP64).  A failed allocation just leaves the copy absent: the builder then keeps gathering.
 void et_data_rowmajor(et_ctx *ctx, et_data *D) {
   if (D->n <= 0 || D->d <= 0 || D->coded == 0) return;
-  const char *env = getenv("ETGPU_SUB_NCLS");  // the subtree builder is opt-in (build.cu)
-  if (!env || atoi(env) <= 0) return;
+  // byte-coded tables always get the row-major copy (k_lane gathers from it); the FP64 one only serves the opt-in
+  // subtree builder (build.cu)
+  const char *env = getenv("ETGPU_SUB_NCLS");
+  const bool sub_on = env && atoi(env) > 0;
+  if (D->coded != 1 && !sub_on) return;
+  if (const char *e2 = getenv("ETGPU_NO_ROWMAJOR"))
+    if (atoi(e2) != 0 && !sub_on) return;
   cudaStream_t st = ctx->stream;
   dim3 block(32, 8), grid((unsigned)ceil_div(D->n, 32), (unsigned)ceil_div(D->d, 32));
   if (D->coded == 1 && !D->r8) {
