@@ -376,8 +376,9 @@ def main():
             traffic = json.load(open(tpath)).get(args.config)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_lane (one warp per node, lane per candidate) + k_node CTA teams: split search + "
-                                          "partition, all size classes of a level on concurrent streams",
+    roofline = {"bound": "hbm", "kernel": "node kernels k_lane (one warp per node, one lane per candidate, row-major byte-code "
+                                          "gathers) + k_node CTA teams: split search + stable partition fused, all size "
+                                          "classes of a level on concurrent streams",
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_step": alg_bytes / args.steps, "kernel_ms_per_step": k_ms / args.steps,
@@ -392,7 +393,9 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg["name"], "trees_per_gpu": m, "rows": n, "features": d, "k": cfg["k"],
                    "n_min": cfg["n_min"], "parallelism": f"tree-sharded x{world}",
-                   "l2": "inputs (table %.0f MB) larger than L2" % (x.nbytes / 1e6)},
+                   "l2": "no flush: the working set of a step (sample-index / label ping-pong buffers %.0f MB + "
+                         "byte-coded table 2 x %.0f MB + FP64 table %.0f MB) is larger than the 126 MB L2"
+                         % (2 * 8 * m * n / 1e6, n * d / 1e6, x.nbytes / 1e6)},
         "e2e": {"value": e2e_value, "unit": "trees/s", "h2d_bytes_per_step": h2d_per_step,
                 "d2h_bytes_per_step": d2h // max(args.steps, 1)},
         "gpu_launches": int(launches),

@@ -1635,6 +1635,9 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
 // and a node of up to 512 samples parks in 16 KB.  NW (32-sample words per node) is a launch
 // parameter: one size class per NW in {1, 2, 4, 8, 16}, shared memory sized to the class.
 constexpr int LANE_WARPS = 4;
+#ifndef LANE_SMALL_CTAS
+#define LANE_SMALL_CTAS 8
+#endif
 
 __host__ __device__ inline int lane_smem_bytes(int task, int C, int W, bool replay, int NW, int vbytes) {
   int o = 0;
@@ -1762,7 +1765,7 @@ __device__ __noinline__ double var_reduction_bits(const uint32_t *s_lt, const ui
 // SMALL: the classes of up to 64 samples run with a tighter register budget (more resident warps; these nodes
 // are dominated by fixed per-batch latency), the larger classes are shared-memory bound anyway.
 template <int TASK, typename VT, bool SMALL>
-__global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? 6 : 4) k_lane(P p, int32_t qcount, int qi, int NW) {
+__global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? LANE_SMALL_CTAS : 4) k_lane(P p, int32_t qcount, int qi, int NW) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool CODED = (sizeof(VT) != 8);
   constexpr uint32_t FULL = 0xffffffffu;
@@ -2003,7 +2006,7 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? 6 : 4) k_lane(P p, in
         for (int w = 0; w < nw; w++) {
           const int j0 = w << 5, cnt = min(32, n - j0);
           const int32_t row = (lane < cnt) ? idx[j0 + lane] : 0;
-          if (cnt == 32) {
+          if (!SMALL && cnt == 32) {  // (the small classes keep their code short: instruction fetch is their top stall)
 #pragma unroll
             for (int jj = 0; jj < 32; jj++) visit(small_tab, __shfl_sync(FULL, row, jj), j0 + jj);
           } else {
