@@ -1913,11 +1913,82 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? LANE_SMALL_CTAS : 4) 
       nconst = nc - (W * 32 - p.d);
       __syncwarp();
     }
+    // Small nodes of a byte-coded table (free-running): which features vary over the node's rows is read off the
+    // rows themselves in the row-major copy (n x 784 contiguous bytes: OR of the XORs with the first row, four
+    // features per word; a NaN byte makes the feature vary like hasMissing does, pkg:236).  Candidates are then
+    // drawn from the varying features only -- the scored candidates of the reference are a uniform sample without
+    // replacement of exactly that set (draws that hit a constant feature are discarded, pkg:236-239), so the split
+    // has the same distribution, and no gather pass is spent on constant features (48 % of the draws before).
+    bool use_nc = false;
+    if (SMALL && CODED && !p.replay && p.R8 != nullptr && p.r8_stride <= 1024) {
+      use_nc = true;
+      const int nword = p.r8_stride >> 2;
+      const uint32_t *cof4 = reinterpret_cast<const uint32_t *>(p.coff);
+      for (int h2 = 0; h2 < 2; h2++) {  // table words lane + 32 i, i = 4 h2 .. 4 h2 + 3
+        if (h2 * 128 >= nword) {
+          for (int w0 = h2 * 16 + lane; w0 < W; w0 += 32) s_taken[w0] = 0xffffffffu;
+          continue;
+        }
+        uint32_t first[4], acc[4];
+        {
+          const uint32_t *rp = reinterpret_cast<const uint32_t *>(p.R8 + (int64_t)idx[0] * p.r8_stride);
+#pragma unroll
+          for (int i4 = 0; i4 < 4; i4++) {
+            const int tw = (h2 * 4 + i4) * 32 + lane;
+            first[i4] = (tw < nword) ? __ldg(rp + tw) : 0u;
+            acc[i4] = 0u;
+          }
+        }
+        for (int w = 0; w < nw; w++) {
+          const int j0 = w << 5, cnt = min(32, n - j0);
+          const int32_t row = (lane < cnt) ? idx[j0 + lane] : 0;
+          for (int jj = (w == 0) ? 1 : 0; jj < cnt; jj++) {
+            const uint32_t *rp =
+                reinterpret_cast<const uint32_t *>(p.R8 + (int64_t)__shfl_sync(FULL, row, jj) * p.r8_stride);
+#pragma unroll
+            for (int i4 = 0; i4 < 4; i4++) {
+              const int tw = (h2 * 4 + i4) * 32 + lane;
+              if (tw < nword) acc[i4] |= __ldg(rp + tw) ^ first[i4];
+            }
+          }
+        }
+#pragma unroll
+        for (int i4 = 0; i4 < 4; i4++) {
+          const int tw = (h2 * 4 + i4) * 32 + lane;
+          uint32_t bits = 0u;
+          if (tw < nword) {
+            const uint32_t k4 = __ldg(cof4 + tw);                                  // 0 = the column holds NaNs
+            const uint32_t nan4 = __vcmpeq4(first[i4], 0u) & __vcmpeq4(k4, 0u);    // the first row is NaN there
+            const uint32_t ne4 = __vcmpne4(acc[i4], 0u) | nan4;                    // 0xff per varying feature
+            bits = ((ne4 & 0x01010101u) * 0x01020408u) >> 24;                      // 4 bits, feature order
+          }
+          uint32_t word = bits << (4 * (lane & 7));
+          word |= __shfl_xor_sync(FULL, word, 1);
+          word |= __shfl_xor_sync(FULL, word, 2);
+          word |= __shfl_xor_sync(FULL, word, 4);
+          const int w0 = (h2 * 4 + i4) * 4 + (lane >> 3);
+          if ((lane & 7) == 0 && w0 < W) s_taken[w0] = ~word;  // taken = not varying (padding included)
+        }
+      }
+      __syncwarp();
+      int nc = 0;
+      for (int w = lane; w < W; w += 32) {
+        const uint32_t m = s_taken[w];
+        s_const[w] = m;  // every feature constant here is constant in the whole subtree
+        nc += __popc(m);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) nc += __shfl_xor_sync(FULL, nc, o);
+      nconst = nc - (W * 32 - p.d);
+      __syncwarp();
+    }
     for (;;) {
       int32_t nb;
       const int32_t avail = p.d - nconst - visited;
       if (p.replay) {
         nb = min(32, tcnt - tpos);
+      } else if (use_nc) {
+        nb = (min(p.k - visited, avail) > 0) ? 32 : 0;
       } else {
         // over-draw by the share of constant features expected among the draws: observed at this node once a
         // batch has been examined; before that, one in two if constants were found on the path from the root
@@ -1945,6 +2016,39 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? LANE_SMALL_CTAS : 4) 
           expect = p.tr.cand_flag[tb + tpos + lane] + 1;
         }
         tpos += nb;
+      } else if (use_nc) {
+        // rounds of draws among the varying features not taken yet; duplicates inside a round lose to the earlier
+        // lane (rejection keeps the sample uniform) and the next round fills up
+        const int32_t want = min(32, p.k - visited);
+        int32_t ncol = 0, left = avail;
+        while (ncol < want && left > 0) {
+          const int32_t nd = min(32, left);
+          int32_t pick = -1 - lane;
+          if (lane < nd)
+            pick = rank_select_clear_fast(s_taken, W, (int32_t)__umul64hi(et_draw(key, (uint32_t)(dc + lane)), (uint64_t)left));
+          dc += 32;
+          const uint32_t same = __match_any_sync(FULL, pick);
+          const bool drawn = lane < nd && lane == __ffs(same) - 1;
+          const uint32_t m_dr = __ballot_sync(FULL, drawn);
+          const int ord = __popc(m_dr & ((1u << lane) - 1u));
+          const bool accp = drawn && ord < want - ncol;
+          const uint32_t m_acc = __ballot_sync(FULL, accp);
+          if (accp) {
+            atomicOr(&s_taken[pick >> 5], 1u << (pick & 31));
+            s_lt[ncol + ord] = (uint32_t)pick;  // (scratch: the side bitmasks are written after the draw)
+          }
+          const int nacc = __popc(m_acc);
+          ncol += nacc;
+          left -= nacc;
+          __syncwarp();
+        }
+        if (ncol == 0) break;
+        if (lane < ncol) {
+          f = (int32_t)s_lt[lane];
+          u = et_u01(et_draw(key, (uint32_t)(dc + lane)));
+        }
+        dc += 32;
+        __syncwarp();
       } else {
         int32_t pick = -1 - lane;
         if (lane < nb) {

@@ -230,7 +230,7 @@ void et_data_drop_codes(et_data *D) {
   et_data_drop_rowmajor(D);
   et_dev_free(D->ctx, D->c8, (size_t)D->d * (size_t)D->ldc);
   et_dev_free(D->ctx, D->dict, (size_t)D->d * 256 * sizeof(double));
-  et_dev_free(D->ctx, D->coff, (size_t)D->d);
+  et_dev_free(D->ctx, D->coff, et_coff_bytes(D->d));
   D->c8 = nullptr;
   D->dict = nullptr;
   D->coff = nullptr;
@@ -252,7 +252,7 @@ void et_data_encode(et_ctx *ctx, et_data *D) {
   D->ldc = ((n + 127) / 128) * 128;
   int32_t *d_cnt = static_cast<int32_t *>(et_dev_alloc(ctx, (size_t)d * sizeof(int32_t)));
   D->dict = static_cast<double *>(et_dev_alloc(ctx, (size_t)d * 256 * sizeof(double)));
-  D->coff = static_cast<uint8_t *>(et_dev_alloc(ctx, (size_t)d));
+  D->coff = static_cast<uint8_t *>(et_dev_alloc(ctx, et_coff_bytes(d)));  // padded with 1 ("no NaN") to whole 16-byte words
   D->c8 = static_cast<uint8_t *>(et_dev_alloc(ctx, (size_t)d * (size_t)D->ldc));
   auto fail = [&](int code, const char *msg) {
     et_dev_free(ctx, d_cnt, (size_t)d * sizeof(int32_t));
@@ -261,6 +261,7 @@ void et_data_encode(et_ctx *ctx, et_data *D) {
     ET_FAIL(code, "%s", msg);
   };
   if (!d_cnt || !D->dict || !D->coff || !D->c8) fail(ET_ENOMEM, "cannot allocate the coded copy of the table");
+  cudaMemsetAsync(D->coff, 1, et_coff_bytes(d), st);
   k_col_dict<<<(unsigned)d, 256, 0, st>>>(D->x, D->ld, n, D->dict, d_cnt, D->coff);
   dim3 grid((unsigned)ceil_div(D->ldc, 1024), (unsigned)d);
   k_col_encode<<<grid, 256, 0, st>>>(D->x, D->ld, n, D->dict, d_cnt, D->coff, D->c8, D->ldc);

@@ -103,6 +103,7 @@ struct BuildArgs {
 };
 
 // encode.cu
+static inline size_t et_coff_bytes(int32_t d) { return ((size_t)d + 15) / 16 * 16 + 16; }
 void et_data_encode(et_ctx *ctx, et_data *data);
 void et_data_drop_codes(et_data *data);  // gives the coded copy back to the context's block cache
 void et_data_rowmajor(et_ctx *ctx, et_data *data);  // row-major copy for the resident subtree builder
