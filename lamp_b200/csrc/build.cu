@@ -49,6 +49,9 @@ constexpr int CTA_TEAM = 512;     // threads of the CTA that owns a larger node
 // (8 B value + 4 B row + 1 B label per sample: 2048 -> 26 KB for the 128-thread team, 8192 -> 104 KB for the
 // 512-thread team, two of which fit one SM)
 __host__ __device__ constexpr int stage_cap(int team) { return team == 32 ? 0 : (team == MID_TEAM ? NM_MAX : 8192); }
+#ifndef CBIG_CTAS
+#define CBIG_CTAS 2
+#endif
 constexpr int CBIG_TEAM = 256;    // threads of the CTA that owns a larger node of a byte-coded table
 constexpr int WARPS_PER_CTA = 4;  // warp teams per CTA in the small-node kernel
 
@@ -195,6 +198,7 @@ struct P {
   // resident subtree builder (subtree.cuh)
   const uint8_t *R8;   // row-major byte codes [n][r8_stride] (also gathered by k_lane)
   int32_t r8_stride;
+  int32_t nc_max;      // k_lane: nodes of up to this many rows draw from their varying-feature set
   const double *XR;    // row-major FP64 [n][sub_rowbytes / 8]
   int32_t sub_ncls;    // size classes 0 .. sub_ncls - 1 are built by k_sub (0: off)
   int32_t sub_rw, sub_rowbytes;  // staged rows per warp, bytes per staged row
@@ -611,7 +615,7 @@ template <int TASK, int TEAM, bool CODED>
 __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
                                   TEAM == 32 ? 5
                                              : (TEAM == MID_TEAM ? (CODED ? 4 : 6)
-                                                                 : ((TASK == TASK_REG && TEAM == CTA_TEAM) ? 1 : 2)))
+                                                                 : ((TASK == TASK_REG && TEAM == CTA_TEAM) ? 1 : ((CODED && TEAM == CBIG_TEAM) ? CBIG_CTAS : 2))))
     k_node(P p, int32_t qcount, int qi) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool WARP = (TEAM == 32);
@@ -1920,7 +1924,7 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? LANE_SMALL_CTAS : 4) 
     // replacement of exactly that set (draws that hit a constant feature are discarded, pkg:236-239), so the split
     // has the same distribution, and no gather pass is spent on constant features (48 % of the draws before).
     bool use_nc = false;
-    if (SMALL && CODED && !p.replay && p.R8 != nullptr && p.r8_stride <= 1024) {
+    if (SMALL && CODED && !p.replay && p.R8 != nullptr && p.r8_stride <= 1024 && n <= p.nc_max) {
       use_nc = true;
       const int nword = p.r8_stride >> 2;
       const uint32_t *cof4 = reinterpret_cast<const uint32_t *>(p.coff);
@@ -2986,6 +2990,8 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
         for (int q = 0; q < NQ - 1; q++) p.cls_max[q] = 0;
       p.R8 = D->r8;
       p.r8_stride = (int32_t)D->rs8;
+      p.nc_max = 64;
+      if (const char *env = getenv("ETGPU_NC_MAX")) p.nc_max = std::max(0, atoi(env));
       p.XR = D->xr;
       p.sub_ncls = 0;
       if (lc.sub_ncls > 0 && lc.sub_from <= 0) {  // the roots themselves may be small enough
