@@ -94,3 +94,43 @@ def test_make_replay_offsets():
     assert r.n_trees == 2 and r.n_cand == 4
     assert keep["node_offset"].tolist() == [0, 3, 6]
     assert keep["cand_begin"].tolist() == [0, 2, 2, 2, 4, 4]
+
+
+# ---- JSON wire format of the tree ADTs (lamp_b200/wire.py; upickle macroRW shape, adt:10-63) -----------------
+def test_wire_format_shape_and_roundtrip():
+    import json
+    import math
+    from lamp_b200 import wire
+    import lamp_b200 as et
+    t = et.ClassificationNonLeaf(et.ClassificationLeaf((1.0, 0.0)),
+                                 et.ClassificationNonLeaf(et.ClassificationLeaf((float("nan"), 0.25)),
+                                                          et.ClassificationLeaf((0.0, 1.0)), 3, -0.0, False),
+                                 0, 97.54668482609304, True)
+    s = wire.tree_to_json(t)
+    o = json.loads(s)
+    assert list(o)[0] == "$type" and o["$type"] == "lamp.extratrees.ClassificationNonLeaf"
+    assert list(o) == ["$type", "left", "right", "splitFeature", "cutpoint", "splitMissingIsLess"]  # constructor order
+    assert o["left"] == {"$type": "lamp.extratrees.ClassificationLeaf", "targetDistribution": [1.0, 0.0]}
+    assert o["right"]["left"]["targetDistribution"][0] == "NaN"  # upickle writes non-finite doubles as strings
+    back = wire.tree_from_json(s)
+    assert back.cutpoint == t.cutpoint and back.splitMissingIsLess and back.right.splitFeature == 3
+    assert math.copysign(1.0, back.right.cutpoint) == -1.0  # -0.0 survives
+    assert math.isnan(back.right.left.targetDistribution[0]) and back.right.right == t.right.right
+    # short type names (upickle 4 default) and whole numbers without a fraction are accepted on input
+    r = wire.tree_from_json('{"$type":"RegressionNonLeaf","left":{"$type":"RegressionLeaf","targetMean":1},'
+                            '"right":{"$type":"RegressionLeaf","targetMean":"-Infinity"},"splitFeature":2,'
+                            '"cutpoint":0.5,"splitMissingIsLess":false}')
+    assert r == et.RegressionNonLeaf(et.RegressionLeaf(1.0), et.RegressionLeaf(float("-inf")), 2, 0.5, False)
+
+
+def test_wire_format_forest_roundtrip_is_bit_exact():
+    from lamp_b200 import wire
+    from lamp_b200.extratrees import FlatTree, flat_to_adt
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(300, 5))
+    y = x[:, 0] * 2 + np.sin(x[:, 1])
+    of = O.build_forest_regression(x, y, 2, 3, 4, 2, seed=7)
+    trees = [flat_to_adt(FlatTree(t.feature, t.cut, t.mil, t.left, t.right, t.leaf), True) for t in of.trees()]
+    back = wire.forest_from_json(wire.forest_to_json(trees))
+    assert back == trees  # dataclass equality: every cutpoint and leaf mean identical as floats
