@@ -490,9 +490,12 @@ __device__ __forceinline__ int32_t rank_select_clear_fast(const uint32_t *taken,
 template <int NG>
 __device__ __forceinline__ void coded_load(const uint8_t *__restrict__ C8, const int64_t *s_coloff, int64_t r,
                                            uint32_t (&b4)[NG]) {
+  // (the byte-coded CTA teams only run on coded tables below 4 GiB: one 32-bit add per load)
+  const uint32_t *off32 = reinterpret_cast<const uint32_t *>(s_coloff);
+  const uint32_t r32 = (uint32_t)r;
   uint32_t b[4 * NG];
 #pragma unroll
-  for (int c = 0; c < 4 * NG; c++) b[c] = __ldg(C8 + s_coloff[c] + r);
+  for (int c = 0; c < 4 * NG; c++) b[c] = __ldg(C8 + (off32[2 * c] + r32));
 #pragma unroll
   for (int g = 0; g < NG; g++) b4[g] = b[4 * g] | (b[4 * g + 1] << 8) | (b[4 * g + 2] << 16) | (b[4 * g + 3] << 24);
 }
@@ -503,18 +506,28 @@ template <int NG, int TEAM>
 __device__ __forceinline__ void coded_pass1(const uint8_t *__restrict__ C8, const int64_t *s_coloff,
                                             const uint32_t *s_K4, const int32_t *rr, int32_t n, int tid,
                                             uint32_t *s_cred, int wit, int lane, uint32_t *s_park) {
-  uint32_t mnT[NG], mxB[NG], mnB[NG], K4[NG];
+  // Two candidates per register as 16-bit halves: sm_100a has native 16x2 min / max / add (VIMNMX.U16x2,
+  // VIADD.16x2), while the 8x4 video intrinsics are emulated with 7-12 logic instructions each.
+  constexpr int NP = 2 * NG;
+  uint32_t mnT[NP], mxB[NP], mnB[NP], K2[NP];
 #pragma unroll
-  for (int g = 0; g < NG; g++) {
-    mnT[g] = 0xffffffffu;
-    mxB[g] = 0u;
-    mnB[g] = 0xffffffffu;
-    K4[g] = s_K4[g];
+  for (int q = 0; q < NP; q++) {
+    mnT[q] = 0xffffffffu;
+    mxB[q] = 0u;
+    mnB[q] = 0xffffffffu;
+    const uint32_t k4 = s_K4[q >> 1] >> (16 * (q & 1));  // bytes 2q, 2q + 1 of the packed K
+    K2[q] = (k4 & 0xffu) | ((k4 & 0xff00u) << 8);
   }
   for (int32_t j = tid; j < n; j += TEAM) {
-    uint32_t b4[NG];
-    coded_load<NG>(C8, s_coloff, (int64_t)rr[j], b4);
+    const uint32_t r32 = (uint32_t)rr[j];
+    const uint32_t *off32 = reinterpret_cast<const uint32_t *>(s_coloff);
+    uint32_t b[4 * NG];
+#pragma unroll
+    for (int c = 0; c < 4 * NG; c++) b[c] = __ldg(C8 + (off32[2 * c] + r32));
     if (s_park) {
+      uint32_t b4[NG];
+#pragma unroll
+      for (int g = 0; g < NG; g++) b4[g] = b[4 * g] | (b[4 * g + 1] << 8) | (b[4 * g + 2] << 16) | (b[4 * g + 3] << 24);
       if (NG >= 4) {
 #pragma unroll
         for (int g = 0; g < NG; g += 4)
@@ -524,24 +537,29 @@ __device__ __forceinline__ void coded_pass1(const uint8_t *__restrict__ C8, cons
       }
     }
 #pragma unroll
-    for (int g = 0; g < NG; g++) {
-      mxB[g] = __vmaxu4(mxB[g], b4[g]);
-      mnB[g] = __vminu4(mnB[g], b4[g]);
-      mnT[g] = __vminu4(mnT[g], __vsub4(b4[g], K4[g]));  // NaN (byte 0 of a column with NaNs) -> 255
+    for (int q = 0; q < NP; q++) {
+      const uint32_t b2 = b[2 * q] | (b[2 * q + 1] << 16);
+      mxB[q] = __vmaxu2(mxB[q], b2);
+      mnB[q] = __vminu2(mnB[q], b2);
+      mnT[q] = __vminu2(mnT[q], __vsub2(b2, K2[q]));  // NaN (byte 0 of a column with NaNs) wraps to 0xffff
     }
   }
 #pragma unroll
-  for (int g = 0; g < NG; g++) {
+  for (int q = 0; q < NP; q++) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      mxB[g] = __vmaxu4(mxB[g], __shfl_xor_sync(0xffffffffu, mxB[g], o));
-      mnB[g] = __vminu4(mnB[g], __shfl_xor_sync(0xffffffffu, mnB[g], o));
-      mnT[g] = __vminu4(mnT[g], __shfl_xor_sync(0xffffffffu, mnT[g], o));
+      mxB[q] = __vmaxu2(mxB[q], __shfl_xor_sync(0xffffffffu, mxB[q], o));
+      mnB[q] = __vminu2(mnB[q], __shfl_xor_sync(0xffffffffu, mnB[q], o));
+      mnT[q] = __vminu2(mnT[q], __shfl_xor_sync(0xffffffffu, mnT[q], o));
     }
-    if (lane == 0) {
-      s_cred[wit * 24 + g] = mnT[g];
-      s_cred[wit * 24 + 8 + g] = mxB[g];
-      s_cred[wit * 24 + 16 + g] = mnB[g];
+    if (lane == 0) {  // back to the byte layout the decode step reads: 4 candidates per word, words g, 8 + g, 16 + g
+      uint8_t *cred8 = reinterpret_cast<uint8_t *>(s_cred + wit * 24);
+      cred8[2 * q] = (uint8_t)min(mnT[q] & 0xffffu, 255u);
+      cred8[2 * q + 1] = (uint8_t)min(mnT[q] >> 16, 255u);
+      cred8[32 + 2 * q] = (uint8_t)(mxB[q] & 0xffu);
+      cred8[32 + 2 * q + 1] = (uint8_t)((mxB[q] >> 16) & 0xffu);
+      cred8[64 + 2 * q] = (uint8_t)min(mnB[q] & 0xffffu, 255u);
+      cred8[64 + 2 * q + 1] = (uint8_t)min(mnB[q] >> 16, 255u);
     }
   }
 }
@@ -2808,7 +2826,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
   lc.smem_cta = (size_t)lay_c.bytes;
   for (int q = 0; q < 5; q++) lc.smem_lane[q] = (size_t)lane_smem_bytes(task, C, W, replay, 1 << q, 1);
   if (lc.coded && lc.smem_lane[4] * LANE_WARPS > 200 * 1024) lc.coded = false;  // (hundreds of classes)
-  lc.coded_big = lc.coded && task == TASK_CLS && C <= 32;
+  lc.coded_big = lc.coded && task == TASK_CLS && C <= 32 && (uint64_t)D->ldc * (uint64_t)d < ((uint64_t)1 << 32);
   if (lc.coded_big) {
     lc.smem_mid = (size_t)make_lay(task, MID_TEAM, C, NB, W, replay, true).bytes;
     lc.smem_cta = (size_t)make_lay(task, CBIG_TEAM, C, NB, W, replay, true).bytes;
