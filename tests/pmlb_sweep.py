@@ -4,10 +4,10 @@ classification tables -- the GPU builder (free-running RNG) next to the CPU orac
 and RNG), same split (test = rows 0..N/3, train = rows N/3+1.., e2e.test.scala:162-165), 100 trees,
 k = floor(sqrt(d)), nMin = 2, a few seeds each.
 
-    python scripts/pmlb_sweep.py [--seeds 5] [--trees 100] [--tables a,b,c] [--out profiles/r1_pmlb_sweep.json]
+    python tests/pmlb_sweep.py [--seeds 5] [--trees 100] [--tables a,b,c] [--out profiles/r1_pmlb_sweep.json]
 
 Prints one line per table: held-out accuracy (mean over seeds) of both, their difference against the tolerance
-max(0.01, 3 SE), and build time per forest.  The oracle is the checker here, never the product path."""
+max(0.01, 3 SE), and build time per forest.  The oracle is the checker here, never the product path (which is why this harness lives under tests/)."""
 import argparse, json, os, sys, time
 import numpy as np
 

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from scripts.pmlb_sweep import load_tables, split
+from tests.pmlb_sweep import load_tables, split
 from tests.helpers import assert_trees_bit_exact, oracle_replay
 
 SMALL = ["vehicle", "led7", "cleve", "optdigits", "dermatology", "segmentation"]
