@@ -566,15 +566,31 @@ __device__ __forceinline__ void coded_pass1(const uint8_t *__restrict__ C8, cons
 
 // pass 2: side histograms.  Per 32 consecutive samples: one ballot per candidate, counted against the
 // class masks with lane == class.  sweep 0 counts x < cut, sweep 1 the NaN samples (pkg:244-248).
+// 32 x 32 bit transpose across a warp: lane r gives row word x (bit c), lane c receives bit r of every row
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) {
+    const uint32_t m = (sft == 16) ? 0x0000ffffu : (sft == 8) ? 0x00ff00ffu : (sft == 4) ? 0x0f0f0f0fu
+                     : (sft == 2) ? 0x33333333u : 0x55555555u;  // bits whose index has bit `sft` clear
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, sft);
+    x = (lane & sft) ? ((x & ~m) | ((y & ~m) >> sft)) : ((x & m) | ((y & m) << sft));
+  }
+  return x;
+}
+
 template <int NG, int TEAM, typename LabFn>
 __device__ __forceinline__ void coded_pass2(const uint8_t *__restrict__ C8, const int64_t *s_coloff,
                                             const uint32_t *s_K4, const uint32_t *s_t4, const uint32_t *s_e4, int sweep,
                                             const int32_t *rr, LabFn lab, int32_t n, int C, int wit, int lane,
                                             int32_t *s_hist, int hs, int hoff, int nb, const uint32_t *s_park) {
-  int32_t acc[4 * NG];
+  // Per 32 consecutive samples: every thread packs the side bits of its sample for all candidates into one word,
+  // one 32 x 32 bit transpose hands lane c the 32 samples' bits of candidate c, and the class counts are
+  // popc(bits & class mask) per class present -- C ballots and C popcounts per 32 samples instead of one ballot and
+  // one popcount per candidate and class mask.  lane == candidate; acc[k] counts class k.
+  int32_t acc[32];
   uint32_t K4[NG], t4[NG], e4[NG];
 #pragma unroll
-  for (int c = 0; c < 4 * NG; c++) acc[c] = 0;
+  for (int k = 0; k < 32; k++) acc[k] = 0;
 #pragma unroll
   for (int g = 0; g < NG; g++) {
     K4[g] = s_K4[g];
@@ -605,27 +621,28 @@ __device__ __forceinline__ void coded_pass2(const uint8_t *__restrict__ C8, cons
     } else {
       coded_load<NG>(C8, s_coloff, valid ? (int64_t)rr[j] : 0, b4);
     }
-    uint32_t cmk = 0u;  // samples of this chunk whose class is this lane's index
-    for (int q2 = 0; q2 < C; q2++) {
-      const uint32_t m = __ballot_sync(0xffffffffu, cls == q2);
-      if (lane == q2) cmk = m;
-    }
+    uint32_t rowbits = 0u;  // bit c: this sample is on the counted side for candidate c
 #pragma unroll
     for (int g = 0; g < NG; g++) {
       uint32_t l4 = sweep ? __vcmpeq4(b4[g], 0u) : __vcmpleu4(__vsub4(b4[g], K4[g]), t4[g]);
       l4 &= e4[g];
-      if (!valid) l4 = 0u;
+      rowbits |= (((l4 & 0x01010101u) * 0x01020408u) >> 24) << (4 * g);
+    }
+    if (!valid) rowbits = 0u;
+    const uint32_t candbits = warp_transpose32(rowbits, lane);  // bit r: sample j0 + r, for candidate `lane`
 #pragma unroll
-      for (int q4 = 0; q4 < 4; q4++) {
-        const uint32_t bal = __ballot_sync(0xffffffffu, (l4 >> (8 * q4)) & 1u);
-        acc[4 * g + q4] += __popc(bal & cmk);
-      }
+    for (int k = 0; k < 32; k++) {
+      if (k >= C) break;
+      const uint32_t cmk = __ballot_sync(0xffffffffu, cls == k);
+      acc[k] += __popc(candbits & cmk);
     }
   }
-  if (lane < C) {
+  if (lane < nb) {
 #pragma unroll
-    for (int c = 0; c < 4 * NG; c++)
-      if (c < nb && acc[c]) atomicAdd(&s_hist[c * hs + hoff + lane], acc[c]);
+    for (int k = 0; k < 32; k++) {
+      if (k >= C) break;
+      if (acc[k]) atomicAdd(&s_hist[lane * hs + hoff + k], acc[k]);
+    }
   }
 }
 
