@@ -11,6 +11,11 @@
 // from creation order to pre-order in shared memory and writes one contiguous block of 16-byte PNodes; the
 // level-wise builder only sees a marker node (feat == -2) that stands for the whole block.
 //
+// Synchronisation inside a team is a producer / consumer protocol on the `nd_ready` flags (record and permutation
+// writes, __threadfence_block, flag store | flag load, __threadfence_block, __syncwarp, reads) and team barriers
+// only between the phases; compute-sanitizer racecheck knows barriers only and reports the flag-ordered accesses as
+// hazards (memcheck is clean, and every parity test runs with this builder on).
+//
 // Table traffic: rows x row bytes ONCE per subtree, against rows x (features examined) x 32-byte sectors
 // per LEVEL of the subtree for the gathering kernels.
 #pragma once
@@ -264,6 +269,7 @@ __global__ void __launch_bounds__(32 * TEAMW, SUB_WARPS / TEAMW) k_sub(P p, int3
     }
     h = __shfl_sync(FULL, h, 0);
     if (h < 0) break;
+    __syncwarp();  // lane 0's acquire (ready flag + fence) orders the whole warp's reads of the node record
 
     const uint32_t be = nd_be[h];
     const int b = (int)(be & 0xffffu), e = (int)(be >> 16), n = e - b;
