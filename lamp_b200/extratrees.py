@@ -433,6 +433,10 @@ def _wrap64(v: int) -> int:
 def _resolve(data, ctx):
     if isinstance(data, DeviceData):
         return data, False
+    if hasattr(data, "indptr") and hasattr(data, "indices") and hasattr(data, "tocsc"):  # a scipy.sparse matrix
+        m = data.tocsc()
+        m.sum_duplicates()
+        return DeviceData.from_csc(m.indptr, m.indices, m.data, m.shape[0], m.shape[1], ctx), True
     return DeviceData.from_rowmajor(data, ctx), True
 
 

@@ -361,6 +361,19 @@ def test_csc_input_builds_the_forest_of_its_dense_expansion():
     dd.free()
 
 
+def test_scipy_sparse_matrix_is_accepted():
+    sp = pytest.importorskip("scipy.sparse")
+    rng = np.random.default_rng(8)
+    dense = np.where(rng.random((3000, 40)) < 0.05, np.round(rng.normal(size=(3000, 40)), 1), 0.0)
+    y = (dense[:, :10].sum(axis=1) > 0).astype(np.int32)
+    f1 = et.buildForestClassification(sp.csc_matrix(dense), y, None, 2, 2, 6, 3, 2, seed=2)
+    f2 = et.buildForestClassification(dense, y, None, 2, 2, 6, 3, 2, seed=2)
+    a, b = f1.export_all(), f2.export_all()
+    for key in ("tree_sizes", "feature", "left", "right", "mil"):
+        assert np.array_equal(a[key], b[key]), key
+    assert np.array_equal(a["cut"].view(np.int64), b["cut"].view(np.int64)) and np.array_equal(a["leaf"], b["leaf"])
+
+
 def test_csc_input_argument_errors():
     with pytest.raises(ValueError):  # row index outside the table
         et.DeviceData.from_csc([0, 1], [7], [1.0], 5, 1)
