@@ -13,8 +13,9 @@
  *
  * Conventions: plain pointers and sizes only.  Every call returns ET_OK or a negative error code;
  * et_last_error() returns the message of the calling thread's last failure.  Host pointers are
- * borrowed for the duration of the call.  Handles are owned by the library until *_free.  One
- * context drives ONE GPU (one process per GPU; trees are sharded across processes by tree id).
+ * borrowed for the duration of the call.  Handles are owned by the library until *_free.  A context
+ * from et_init drives ONE GPU; a context from et_init_multi drives several GPUs of one box from one
+ * process (trees sharded by tree id, NCCL over NVLink inside the library), behind the same calls.
  * There is NO CPU fallback: without a CUDA device et_init fails.
  */
 #ifndef ETGPU_H
@@ -32,6 +33,7 @@ extern "C" {
 #define ET_ENOMEM (-3)   /* device or host allocation failed */
 #define ET_EREPLAY (-4)  /* replay trace does not fit the data (test hook misuse) */
 #define ET_EUNSUPPORTED (-5)
+#define ET_ENCCL (-6)    /* NCCL failure / libnccl.so.2 not loadable (multi-GPU calls only) */
 
 typedef struct et_ctx et_ctx;
 typedef struct et_data et_data;
@@ -44,6 +46,22 @@ const char *et_last_error(void);
 /* ---- context ------------------------------------------------------------------------------ */
 /* One context per GPU.  Replaces the reference's hidden cats-effect global runtime (pkg:6,656,675). */
 int et_init(int32_t device, et_ctx **out);
+/* Several GPUs of one box behind ONE context (replaces parTraverseN(parallelism), pkg:653-675: the fan-out
+ * stays hidden inside the call).  One host thread per GPU, ncclCommInitAll over the given devices.  Every call
+ * of this header then works on the multi-GPU context:
+ *   et_data_*            one host->device upload to the first GPU, ncclBroadcast over NVLink to the others
+ *                        (every GPU holds a replica of the table); targets / weights go to every GPU
+ *   et_build_*           tree t of the forest is built by GPU t mod G (a tree's random stream depends only on
+ *                        (seed, tree id): the forest equals the one a single GPU builds); the serialized trees
+ *                        are all-gathered (ncclAllGather of sizes, grouped ncclBroadcast of the packed nodes),
+ *                        so every GPU -- and the host, through et_forest_export* -- holds the whole forest
+ *   et_predict_*         trees stay sharded: every GPU traverses all rows for its trees, the per-row partial
+ *                        sums are all-reduced (ncclAllReduce, FP64 sum) and divided by m once.  The sum is
+ *                        re-associated across GPUs: results agree with the single-GPU / reference value to
+ *                        ~1e-15 relative (inside the 1e-12 bar), not bit for bit.
+ * The replay test hook is single-GPU only (ET_EUNSUPPORTED here). */
+int et_init_multi(const int32_t *devices, int32_t n_devices, et_ctx **out);
+int32_t et_device_count(const et_ctx *ctx);
 void et_shutdown(et_ctx *ctx);
 /* Run all work of this context on the caller's CUDA stream (cudaStream_t passed as void*); NULL
  * restores the context's own stream.  Lets a host framework time the library with its own events. */
@@ -129,7 +147,8 @@ typedef struct et_stats {
 
 /* ---- build ---------------------------------------------------------------------------------
  * Replaces buildForestClassification (pkg:611-681) / buildForestRegression (pkg:704-764).
- * target/weights: host arrays uploaded for this call, or NULL to use the ones attached to `data`.
+ * target/weights: host arrays uploaded for this call (and left attached to `data`), or NULL to use the ones
+ * attached to `data`; the two are independent (et_data_set_weights(.., NULL, 0) detaches weights).
  * parallelism selects the reference's SEEDING SCHEME (pkg:634 vs 654-655), not the GPU's
  * parallelism.  tree_ids (m entries, NULL = 0..m-1) are the global indices of the trees this GPU
  * builds: a tree's random stream depends only on (seed, tree id), so a forest sharded over G GPUs
@@ -192,6 +211,28 @@ int et_predict_classification_device(et_ctx *ctx, et_forest *f, const double *x_
                                      int64_t n, int32_t d, double *out_dev, int32_t sum_only);
 int et_predict_regression_device(et_ctx *ctx, et_forest *f, const double *x_rowmajor_dev, int64_t n,
                                  int32_t d, double *out_dev, int32_t sum_only);
+
+/* ---- one process per GPU (torchrun / MPI style launchers) ------------------------------------------------
+ * The same collectives for callers that run one PROCESS per GPU: rank 0 creates a 128-byte NCCL unique id, the
+ * launcher's own channel (torch.distributed, MPI, a file) hands it to the other ranks, and every rank attaches a
+ * communicator to its single-GPU context.  The caller shards the trees itself (tree_ids of et_build_*). */
+#define ET_COMM_ID_BYTES 128
+int et_comm_unique_id(uint8_t *id_out);
+int et_comm_init_rank(et_ctx *ctx, int32_t world, int32_t rank, const uint8_t *id);
+/* Replicates a resident table from rank `root` to every rank over NVLink (ncclBroadcast): `data` is the table
+ * on the root rank and NULL elsewhere; every rank gets a handle in *out (the root gets `data` itself). */
+int et_data_broadcast(et_ctx *ctx, et_data *data, int32_t root, et_data **out);
+/* All-gather of the serialized trees: every rank passes the forest of its own trees and gets the whole forest,
+ * trees ordered by their global tree id (the tree_ids the shards were built with). */
+int et_forest_allgather(et_ctx *ctx, et_forest *shard, et_forest **full);
+/* Tree-sharded predict on device buffers: partial sums over this rank's trees, ncclAllReduce(sum) in row chunks
+ * overlapped with the traversal, one division by m_total (the forest's tree count over all ranks). */
+int et_predict_classification_allreduce(et_ctx *ctx, et_forest *shard, const double *x_rowmajor_dev, int64_t n,
+                                        int32_t d, double *out_dev, int32_t m_total);
+int et_predict_regression_allreduce(et_ctx *ctx, et_forest *shard, const double *x_rowmajor_dev, int64_t n,
+                                    int32_t d, double *out_dev, int32_t m_total);
+/* Device time of the collectives queued by the last gather / all-reduce call of this context (ms). */
+double et_comm_last_ms(const et_ctx *ctx);
 
 /* ---- test hooks (host-side arithmetic shared with the kernels) ------------------------------ */
 /* Value of adding `c` to 0.0 `h` times in round-to-nearest FP64 -- the closed form the kernels use

@@ -8,8 +8,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libetgpu.so")
 
-ET_OK, ET_EINVAL, ET_ECUDA, ET_ENOMEM, ET_EREPLAY, ET_EUNSUPPORTED = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 1
+ET_OK, ET_EINVAL, ET_ECUDA, ET_ENOMEM, ET_EREPLAY, ET_EUNSUPPORTED, ET_ENCCL = 0, -1, -2, -3, -4, -5, -6
+ABI_VERSION = 2
+COMM_ID_BYTES = 128
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int32)
@@ -45,6 +46,8 @@ SIGNATURES = {
     "et_abi_version": (C.c_int32, []),
     "et_last_error": (C.c_char_p, []),
     "et_init": (C.c_int, [C.c_int32, C.POINTER(vp)]),
+    "et_init_multi": (C.c_int, [ip, C.c_int32, C.POINTER(vp)]),
+    "et_device_count": (C.c_int32, [vp]),
     "et_shutdown": (None, [vp]),
     "et_set_stream": (C.c_int, [vp, vp]),
     "et_synchronize": (C.c_int, [vp]),
@@ -78,6 +81,13 @@ SIGNATURES = {
     "et_predict_regression": (C.c_int, [vp, vp, dp, C.c_int64, C.c_int32, dp, C.c_int32]),
     "et_predict_classification_device": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int32, vp, C.c_int32]),
     "et_predict_regression_device": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int32, vp, C.c_int32]),
+    "et_comm_unique_id": (C.c_int, [bp]),
+    "et_comm_init_rank": (C.c_int, [vp, C.c_int32, C.c_int32, bp]),
+    "et_data_broadcast": (C.c_int, [vp, vp, C.c_int32, C.POINTER(vp)]),
+    "et_forest_allgather": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "et_predict_classification_allreduce": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int32, vp, C.c_int32]),
+    "et_predict_regression_allreduce": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int32, vp, C.c_int32]),
+    "et_comm_last_ms": (C.c_double, [vp]),
     "et_debug_repeat_add": (C.c_double, [C.c_double, C.c_int64]),
 }
 

@@ -105,8 +105,6 @@ extern "C" int et_init(int32_t device, et_ctx **out) {
   et_ctx *c = new et_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  // the level loop (own stream + the side streams of its size classes) runs at high priority; the asynchronous
-  // resident-subtree kernels run on low-priority streams and fill the SMs the level loop leaves idle
   int prio_least = 0, prio_greatest = 0;
   CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
   CUDA_CHECK(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, prio_greatest));
@@ -116,15 +114,17 @@ extern "C" int et_init(int32_t device, et_ctx **out) {
     CUDA_CHECK(cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, prio_greatest));
     CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
   }
-  for (int q = 0; q < et_ctx::N_SUB_CLS; q++)
-    for (int r = 0; r < et_ctx::N_SUB_RING; r++)
-      CUDA_CHECK(cudaStreamCreateWithPriority(&c->sub_stream[q][r], cudaStreamNonBlocking, prio_least));
   *out = c;
   ET_API_END
 }
 
 extern "C" void et_shutdown(et_ctx *ctx) {
   if (!ctx) return;
+  if (ctx->is_multi()) {
+    et_multi_shutdown(ctx);
+    delete ctx;
+    return;
+  }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -133,9 +133,8 @@ extern "C" void et_shutdown(et_ctx *ctx) {
     if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-  for (int q = 0; q < et_ctx::N_SUB_CLS; q++)
-    for (int r = 0; r < et_ctx::N_SUB_RING; r++)
-      if (ctx->sub_stream[q][r]) cudaStreamDestroy(ctx->sub_stream[q][r]);
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
   et_workspace_free(ctx->ws);
   for (auto &b : ctx->cache) cudaFree(b.p);
   delete ctx;
@@ -144,6 +143,7 @@ extern "C" void et_shutdown(et_ctx *ctx) {
 extern "C" int et_set_stream(et_ctx *ctx, void *cuda_stream) {
   ET_API_BEGIN
   if (!ctx) ET_FAIL(ET_EINVAL, "et_set_stream: ctx is NULL");
+  if (ctx->is_multi()) ET_FAIL(ET_EUNSUPPORTED, "et_set_stream: a multi-GPU context runs on its own streams");
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   ET_API_END
@@ -152,6 +152,13 @@ extern "C" int et_set_stream(et_ctx *ctx, void *cuda_stream) {
 extern "C" int et_synchronize(et_ctx *ctx) {
   ET_API_BEGIN
   if (!ctx) ET_FAIL(ET_EINVAL, "et_synchronize: ctx is NULL");
+  if (ctx->is_multi()) {
+    for (et_ctx *c : ctx->peers) {
+      CUDA_CHECK(cudaSetDevice(c->device));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    return ET_OK;
+  }
   CUDA_CHECK(cudaSetDevice(ctx->device));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   ET_API_END
@@ -188,7 +195,30 @@ void et_launch_transpose(et_ctx *ctx, const double *src, int64_t rows, int32_t d
 }
 
 // ---- data -----------------------------------------------------------------------------------
-static et_data *data_alloc(et_ctx *ctx, int64_t n, int32_t d) {
+et_data *et_data_alloc_internal(et_ctx *ctx, int64_t n, int32_t d);
+static et_data *data_alloc(et_ctx *ctx, int64_t n, int32_t d) { return et_data_alloc_internal(ctx, n, d); }
+
+// front handle of a table replicated on every GPU of a multi-GPU context: made from the first GPU's table
+static et_data *multi_front_data(et_ctx *front, et_data *d0, bool replicate) {
+  et_data *F = new et_data();
+  F->ctx = front;
+  F->n = d0->n;
+  F->d = d0->d;
+  F->ld = d0->ld;
+  F->shards.push_back(d0);
+  if (replicate) {
+    try {
+      et_multi_replicate(front, F);
+    } catch (...) {
+      et_data_free(d0);
+      delete F;
+      throw;
+    }
+  }
+  return F;
+}
+
+et_data *et_data_alloc_internal(et_ctx *ctx, int64_t n, int32_t d) {
   if (n < 0 || d < 0) ET_FAIL(ET_EINVAL, "negative table dimensions");
   if (n > 0x7fffffff) ET_FAIL(ET_EUNSUPPORTED, "tables with more than 2^31-1 rows are not supported");
   et_data *D = new et_data();
@@ -209,6 +239,27 @@ static et_data *data_alloc(et_ctx *ctx, int64_t n, int32_t d) {
 extern "C" int et_data_dense_alloc(et_ctx *ctx, int64_t n, int32_t d, et_data **out) {
   ET_API_BEGIN
   if (!ctx || !out) ET_FAIL(ET_EINVAL, "et_data_dense_alloc: NULL argument");
+  if (ctx->is_multi()) {
+    et_data *F = new et_data();
+    F->ctx = ctx;
+    try {
+      for (et_ctx *c : ctx->peers) {
+        et_data *r = nullptr;
+        int rc = et_data_dense_alloc(c, n, d, &r);
+        if (rc != ET_OK) throw EtError{rc};
+        F->shards.push_back(r);
+      }
+    } catch (...) {
+      for (et_data *r : F->shards) et_data_free(r);
+      delete F;
+      throw;
+    }
+    F->n = n;
+    F->d = d;
+    F->ld = F->shards[0]->ld;
+    *out = F;
+    return ET_OK;
+  }
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   *out = data_alloc(ctx, n, d);
@@ -219,6 +270,13 @@ extern "C" int et_data_dense_colblock(et_ctx *ctx, et_data *D, const double *col
                                       int32_t n_cols) {
   ET_API_BEGIN
   if (!ctx || !D || (!cols && n_cols > 0)) ET_FAIL(ET_EINVAL, "et_data_dense_colblock: NULL argument");
+  if (ctx->is_multi()) {  // host -> first GPU, then NVLink to the others
+    if (D->shards.size() != ctx->peers.size()) ET_FAIL(ET_EINVAL, "et_data_dense_colblock: not a table of this context");
+    int rc = et_data_dense_colblock(ctx->peers[0], D->shards[0], cols, first_col, n_cols);
+    if (rc != ET_OK) return rc;
+    et_multi_broadcast_columns(ctx, D, first_col, n_cols);
+    return ET_OK;
+  }
   if (first_col < 0 || n_cols < 0 || first_col + n_cols > D->d)
     ET_FAIL(ET_EINVAL, "et_data_dense_colblock: columns [%d,%d) outside [0,%d)", first_col, first_col + n_cols, D->d);
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
@@ -238,6 +296,13 @@ extern "C" int et_data_dense_colblock(et_ctx *ctx, et_data *D, const double *col
 extern "C" int et_data_dense_rowmajor(et_ctx *ctx, const double *x, int64_t n, int32_t d, et_data **out) {
   ET_API_BEGIN
   if (!ctx || !out || (!x && n > 0 && d > 0)) ET_FAIL(ET_EINVAL, "et_data_dense_rowmajor: NULL argument");
+  if (ctx->is_multi()) {  // one upload to the first GPU, replicas over NVLink
+    et_data *d0 = nullptr;
+    int rc = et_data_dense_rowmajor(ctx->peers[0], x, n, d, &d0);
+    if (rc != ET_OK) return rc;
+    *out = multi_front_data(ctx, d0, true);
+    return ET_OK;
+  }
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   et_data *D = data_alloc(ctx, n, d);
@@ -275,6 +340,7 @@ extern "C" int et_data_dense_rowmajor_device(et_ctx *ctx, const double *x_dev, i
                                              et_data **out) {
   ET_API_BEGIN
   if (!ctx || !out || (!x_dev && n > 0 && d > 0)) ET_FAIL(ET_EINVAL, "et_data_dense_rowmajor_device: NULL argument");
+  if (ctx->is_multi()) ET_FAIL(ET_EUNSUPPORTED, "device-pointer inputs need a single-GPU context");
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   et_data *D = data_alloc(ctx, n, d);
@@ -311,6 +377,13 @@ extern "C" int et_data_csc(et_ctx *ctx, const int64_t *colptr, const int32_t *ro
                            int32_t d, et_data **out) {
   ET_API_BEGIN
   if (!ctx || !out || !colptr) ET_FAIL(ET_EINVAL, "et_data_csc: NULL argument");
+  if (ctx->is_multi()) {
+    et_data *d0 = nullptr;
+    int rc = et_data_csc(ctx->peers[0], colptr, rowidx, val, n, d, &d0);
+    if (rc != ET_OK) return rc;
+    *out = multi_front_data(ctx, d0, true);
+    return ET_OK;
+  }
   if (n < 0 || d < 0) ET_FAIL(ET_EINVAL, "negative table dimensions");
   if (colptr[0] != 0) ET_FAIL(ET_EINVAL, "et_data_csc: colptr[0] must be 0");
   for (int32_t c = 0; c < d; c++)
@@ -386,6 +459,14 @@ extern "C" int et_data_set_target_classification(et_ctx *ctx, et_data *D, const 
                                                  int32_t num_classes) {
   ET_API_BEGIN
   if (!ctx || !D || (!y && n_target > 0)) ET_FAIL(ET_EINVAL, "et_data_set_target_classification: NULL argument");
+  if (ctx->is_multi()) {
+    for (size_t g = 0; g < D->shards.size(); g++) {
+      int rc = et_data_set_target_classification(ctx->peers[g], D->shards[g], y, n_target, num_classes);
+      if (rc != ET_OK) return rc;
+    }
+    D->num_classes = num_classes;
+    return ET_OK;
+  }
   if (n_target != D->n)
     ET_FAIL(ET_EINVAL, "requirement failed: Data.numRows(%lld) != target.length (%lld)", (long long)D->n,
             (long long)n_target);
@@ -408,6 +489,13 @@ extern "C" int et_data_set_target_classification(et_ctx *ctx, et_data *D, const 
 extern "C" int et_data_set_target_regression(et_ctx *ctx, et_data *D, const double *y, int64_t n_target) {
   ET_API_BEGIN
   if (!ctx || !D || (!y && n_target > 0)) ET_FAIL(ET_EINVAL, "et_data_set_target_regression: NULL argument");
+  if (ctx->is_multi()) {
+    for (size_t g = 0; g < D->shards.size(); g++) {
+      int rc = et_data_set_target_regression(ctx->peers[g], D->shards[g], y, n_target);
+      if (rc != ET_OK) return rc;
+    }
+    return ET_OK;
+  }
   if (n_target != D->n)
     ET_FAIL(ET_EINVAL, "requirement failed: Data.numRows(%lld) != target.length (%lld)", (long long)D->n,
             (long long)n_target);
@@ -420,6 +508,13 @@ extern "C" int et_data_set_target_regression(et_ctx *ctx, et_data *D, const doub
 extern "C" int et_data_set_weights(et_ctx *ctx, et_data *D, const double *w, int64_t n_weights) {
   ET_API_BEGIN
   if (!ctx || !D) ET_FAIL(ET_EINVAL, "et_data_set_weights: NULL argument");
+  if (ctx->is_multi()) {
+    for (size_t g = 0; g < D->shards.size(); g++) {
+      int rc = et_data_set_weights(ctx->peers[g], D->shards[g], w, n_weights);
+      if (rc != ET_OK) return rc;
+    }
+    return ET_OK;
+  }
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   if (!w) {
@@ -447,6 +542,11 @@ extern "C" int et_data_dims(const et_data *D, int64_t *n, int32_t *d) {
 
 extern "C" void et_data_free(et_data *D) {
   if (!D) return;
+  if (!D->shards.empty()) {  // front handle of a multi-GPU table
+    for (et_data *r : D->shards) et_data_free(r);
+    delete D;
+    return;
+  }
   if (D->ctx) cudaSetDevice(D->ctx->device);
   std::unique_lock<std::recursive_mutex> lk;
   if (D->ctx) lk = std::unique_lock<std::recursive_mutex>(D->ctx->mu);
@@ -473,10 +573,42 @@ extern "C" int et_build_classification(et_ctx *ctx, et_data *D, const int32_t *t
                                        et_forest **out, et_stats *stats) {
   ET_API_BEGIN
   check_build_common(ctx, D, k, m, best_split, out);
+  if (ctx->is_multi()) {
+    if (target) {
+      int rc = et_data_set_target_classification(ctx, D, target, n_target, num_classes);
+      if (rc != ET_OK) return rc;
+    }
+    if (weights) {
+      int rc = et_data_set_weights(ctx, D, weights, target ? n_target : D->n);
+      if (rc != ET_OK) return rc;
+    }
+    et_data *d0 = D->shards.empty() ? nullptr : D->shards[0];
+    if (!d0 || !d0->y_cls) ET_FAIL(ET_EINVAL, "build: no classification target attached");
+    if (d0->num_classes != num_classes) ET_FAIL(ET_EINVAL, "build: numClasses differs from the attached target's");
+    if (D->n == 0 && m > 0) ET_FAIL(ET_EINVAL, "build: empty table (the reference fails on targetInSubset.raw(0))");
+    BuildArgs a;
+    a.task = d0->w ? 1 : 0;
+    a.num_classes = num_classes;
+    a.n_min = n_min;
+    a.k = k;
+    a.m = m;
+    a.parallelism = parallelism;
+    a.best_split = best_split;
+    a.max_depth = max_depth;
+    a.seed = seed;
+    a.tree_ids = tree_ids;
+    a.replay = replay;
+    et_multi_build(ctx, D, a, num_classes, 0, out, stats);
+    return ET_OK;
+  }
+  // target and weights are independent: each is either uploaded for this call or, when NULL, the one attached
+  // to `data` is used (et_data_set_weights(NULL) is the way to detach weights)
   if (target) {
     int rc = et_data_set_target_classification(ctx, D, target, n_target, num_classes);
     if (rc != ET_OK) return rc;
-    rc = et_data_set_weights(ctx, D, weights, weights ? n_target : 0);
+  }
+  if (weights) {
+    int rc = et_data_set_weights(ctx, D, weights, target ? n_target : D->n);
     if (rc != ET_OK) return rc;
   }
   if (!D->y_cls) ET_FAIL(ET_EINVAL, "build: no classification target attached");
@@ -521,6 +653,25 @@ extern "C" int et_build_regression(et_ctx *ctx, et_data *D, const double *target
     int rc = et_data_set_target_regression(ctx, D, target, n_target);
     if (rc != ET_OK) return rc;
   }
+  if (ctx->is_multi()) {
+    et_data *d0 = D->shards.empty() ? nullptr : D->shards[0];
+    if (!d0 || !d0->y_reg) ET_FAIL(ET_EINVAL, "build: no regression target attached");
+    if (D->n == 0 && m > 0) ET_FAIL(ET_EINVAL, "requirement failed (subset.length > 0, pkg:779)");
+    BuildArgs a;
+    a.task = 2;
+    a.num_classes = 1;
+    a.n_min = n_min;
+    a.k = k;
+    a.m = m;
+    a.parallelism = parallelism;
+    a.best_split = best_split;
+    a.max_depth = max_depth;
+    a.seed = seed;
+    a.tree_ids = tree_ids;
+    a.replay = replay;
+    et_multi_build(ctx, D, a, 1, 1, out, stats);
+    return ET_OK;
+  }
   if (!D->y_reg) ET_FAIL(ET_EINVAL, "build: no regression target attached");
   if (D->n == 0 && m > 0) ET_FAIL(ET_EINVAL, "requirement failed (subset.length > 0, pkg:779)");
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
@@ -554,6 +705,11 @@ extern "C" int et_build_regression(et_ctx *ctx, et_data *D, const double *target
 
 // ---- forest ---------------------------------------------------------------------------------
 et_forest::~et_forest() {
+  if (!shards.empty() || full) {  // front handle of a multi-GPU forest
+    for (et_forest *s : shards) delete s;
+    delete full;
+    return;
+  }
   if (ctx) cudaSetDevice(ctx->device);
   if (d_tree_off) cudaFree(d_tree_off);
   std::unique_lock<std::recursive_mutex> lk;
@@ -573,6 +729,13 @@ extern "C" void et_forest_free(et_forest *f) { delete f; }
 // The forest lives in HBM; the host copy is fetched on first export.
 void et_forest_fetch(et_forest *f) {
   if (f->host_ready) return;
+  if (f->full) {  // multi-GPU front handle: the gathered forest on the first GPU
+    et_forest_fetch(f->full);
+    f->h_nodes = f->full->h_nodes;
+    f->h_leaf = f->full->h_leaf;
+    f->host_ready = true;
+    return;
+  }
   std::lock_guard<std::recursive_mutex> lk(f->ctx->mu);
   if (f->host_ready) return;
   CUDA_CHECK(cudaSetDevice(f->ctx->device));
@@ -668,6 +831,23 @@ extern "C" int et_forest_import(et_ctx *ctx, int32_t m, int32_t leaf_width, int3
                                 et_forest **out) {
   ET_API_BEGIN
   if (!ctx || !out || m < 0 || leaf_width <= 0) ET_FAIL(ET_EINVAL, "et_forest_import: bad argument");
+  if (ctx->is_multi()) {  // host-held trees live on the first GPU (predict then runs there)
+    et_forest *f0 = nullptr;
+    int rc = et_forest_import(ctx->peers[0], m, leaf_width, is_regression, tree_sizes, feature, cut, mil, left, right, leaf, &f0);
+    if (rc != ET_OK) return rc;
+    et_forest *F = new et_forest();
+    F->ctx = ctx;
+    F->leaf_width = leaf_width;
+    F->is_regression = is_regression;
+    F->m = m;
+    F->full = f0;
+    F->total_nodes = f0->total_nodes;
+    F->total_leaves = f0->total_leaves;
+    F->tree_off = f0->tree_off;
+    F->d_min = f0->d_min;
+    *out = F;
+    return ET_OK;
+  }
   if (m > 0 && (!tree_sizes || !feature || !cut || !mil || !left || !right || !leaf))
     ET_FAIL(ET_EINVAL, "et_forest_import: NULL array");
   std::unique_ptr<et_forest> f(new et_forest());
@@ -693,6 +873,7 @@ extern "C" int et_forest_import(et_ctx *ctx, int32_t m, int32_t leaf_width, int3
         if (left[off + i] != i + 1 || right[off + i] <= i + 1 || right[off + i] >= n)
           ET_FAIL(ET_EINVAL, "et_forest_import: tree %d node %lld is not in pre-order", t, (long long)i);
         if (feature[off + i] >= ET_MIL_BIT) ET_FAIL(ET_EINVAL, "et_forest_import: feature index too large");
+        f->d_min = std::max(f->d_min, feature[off + i] + 1);
         p.feat = feature[off + i] | (mil[off + i] ? ET_MIL_BIT : 0);
         p.right_or_leaf = right[off + i];
       } else {
@@ -739,6 +920,7 @@ extern "C" int et_forest_packed_dims(const et_forest *f, int64_t *total_nodes, i
 extern "C" int et_forest_export_packed(et_forest *f, void *nodes_out, double *leaves_out, int64_t *tree_off_out) {
   ET_API_BEGIN
   if (!f || !nodes_out || !leaves_out || !tree_off_out) ET_FAIL(ET_EINVAL, "et_forest_export_packed: NULL argument");
+  if (f->full) return et_forest_export_packed(f->full, nodes_out, leaves_out, tree_off_out);
   std::lock_guard<std::recursive_mutex> lk(f->ctx->mu);
   CUDA_CHECK(cudaSetDevice(f->ctx->device));
   cudaStream_t st = f->ctx->stream;
@@ -758,10 +940,29 @@ extern "C" int et_forest_import_packed(et_ctx *ctx, int32_t m, int32_t leaf_widt
   ET_API_BEGIN
   if (!ctx || !out || m < 0 || leaf_width <= 0 || total_nodes < 0 || total_leaves < 0 || !tree_off)
     ET_FAIL(ET_EINVAL, "et_forest_import_packed: bad argument");
+  if (ctx->is_multi()) {
+    et_forest *f0 = nullptr;
+    int rc = et_forest_import_packed(ctx->peers[0], m, leaf_width, is_regression, total_nodes, total_leaves, nodes, leaves,
+                                     tree_off, &f0);
+    if (rc != ET_OK) return rc;
+    et_forest *F = new et_forest();
+    F->ctx = ctx;
+    F->leaf_width = leaf_width;
+    F->is_regression = is_regression;
+    F->m = m;
+    F->full = f0;
+    F->total_nodes = f0->total_nodes;
+    F->total_leaves = f0->total_leaves;
+    F->tree_off = f0->tree_off;
+    F->d_min = f0->d_min;
+    *out = F;
+    return ET_OK;
+  }
   if ((total_nodes > 0 && !nodes) || (total_leaves > 0 && !leaves))
     ET_FAIL(ET_EINVAL, "et_forest_import_packed: NULL array");
   if (tree_off[0] != 0 || tree_off[m] != total_nodes) ET_FAIL(ET_EINVAL, "et_forest_import_packed: bad tree offsets");
   const PNode *pn = static_cast<const PNode *>(nodes);
+  int32_t d_min = 0;
   for (int32_t t = 0; t < m; t++) {
     const int64_t off = tree_off[t], n = tree_off[t + 1] - off;
     if (n <= 0) ET_FAIL(ET_EINVAL, "et_forest_import_packed: tree %d is empty", t);
@@ -770,6 +971,9 @@ extern "C" int et_forest_import_packed(et_ctx *ctx, int32_t m, int32_t leaf_widt
       if (q.feat >= 0) {
         if (q.right_or_leaf <= i + 1 || q.right_or_leaf >= n)
           ET_FAIL(ET_EINVAL, "et_forest_import_packed: tree %d node %lld is not in pre-order", t, (long long)i);
+        d_min = std::max(d_min, (q.feat & (ET_MIL_BIT - 1)) + 1);
+      } else if (q.feat != -1) {
+        ET_FAIL(ET_EINVAL, "et_forest_import_packed: tree %d node %lld: bad feature field", t, (long long)i);
       } else if (q.right_or_leaf < 0 || q.right_or_leaf >= total_leaves) {
         ET_FAIL(ET_EINVAL, "et_forest_import_packed: tree %d node %lld: leaf index out of range", t, (long long)i);
       }
@@ -783,6 +987,7 @@ extern "C" int et_forest_import_packed(et_ctx *ctx, int32_t m, int32_t leaf_widt
   f->tree_off.assign(tree_off, tree_off + m + 1);
   f->total_nodes = total_nodes;
   f->total_leaves = total_leaves;
+  f->d_min = d_min;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   CUDA_CHECK(cudaMalloc((void **)&f->d_tree_off, ((size_t)m + 1) * sizeof(int64_t)));
@@ -801,11 +1006,24 @@ extern "C" int et_forest_import_packed(et_ctx *ctx, int32_t m, int32_t leaf_widt
 }
 
 // ---- predict --------------------------------------------------------------------------------
+void et_predict_host_impl(et_ctx *ctx, et_forest *f, const double *x, int64_t n, int32_t d, double *out, int sum_only,
+                          int want_regression);
 static void predict_host(et_ctx *ctx, et_forest *f, const double *x, int64_t n, int32_t d, double *out,
                          int sum_only, int want_regression) {
   if (!ctx || !f || (!x && n > 0 && d > 0) || (!out && n > 0)) ET_FAIL(ET_EINVAL, "predict: NULL argument");
+  if (n < 0 || d < 0) ET_FAIL(ET_EINVAL, "predict: negative dimensions");
+  if (ctx->is_multi())
+    et_multi_predict(ctx, f, x, n, d, out, sum_only, want_regression);
+  else
+    et_predict_host_impl(ctx, f, x, n, d, out, sum_only, want_regression);
+}
+
+void et_predict_host_impl(et_ctx *ctx, et_forest *f, const double *x, int64_t n, int32_t d, double *out, int sum_only,
+                          int want_regression) {
   if (f->is_regression != want_regression) ET_FAIL(ET_EINVAL, "predict: forest kind does not match the call");
   if (n < 0 || d < 0) ET_FAIL(ET_EINVAL, "predict: negative dimensions");
+  if (n > 0 && d < f->d_min)  // (ArrayIndexOutOfBounds in the reference, pkg:517)
+    ET_FAIL(ET_EINVAL, "predict: samples have %d features, the forest splits on feature %d", d, f->d_min - 1);
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   if (n == 0) return;
@@ -857,7 +1075,10 @@ extern "C" int et_predict_regression(et_ctx *ctx, et_forest *f, const double *x,
 static void predict_dev(et_ctx *ctx, et_forest *f, const double *x, int64_t n, int32_t d, double *out, int sum_only,
                         int want_regression) {
   if (!ctx || !f || (!x && n > 0 && d > 0) || (!out && n > 0)) ET_FAIL(ET_EINVAL, "predict: NULL argument");
+  if (ctx->is_multi()) ET_FAIL(ET_EUNSUPPORTED, "device-pointer inputs need a single-GPU context");
   if (f->is_regression != want_regression) ET_FAIL(ET_EINVAL, "predict: forest kind does not match the call");
+  if (n > 0 && d < f->d_min)
+    ET_FAIL(ET_EINVAL, "predict: samples have %d features, the forest splits on feature %d", d, f->d_min - 1);
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   if (n <= 0) return;

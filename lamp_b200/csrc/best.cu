@@ -1,4 +1,4 @@
-// best.cuh -- bestSplit = true (included by build.cu inside its anonymous namespace).
+// best.cu -- bestSplit = true.
 //
 // splitBestClassification (pkg:56-202) / splitBestRegression (pkg:298-426): for every drawn non-constant
 // feature EVERY sample value of the node is tried as the cutpoint (score(i) for i = 0 .. n-1 in subset order, the
@@ -14,7 +14,9 @@
 //   k_best_finish   CTA per node    leaf | stable partition (pkg:1024-1039) and the two children
 //
 // Tables are read as FP64 (column-major X); this path is the reference's secondary variant.
-#pragma once
+#include "build.cuh"
+
+namespace etb {
 
 struct BestState {  // search state per open node of the level (SoA over the frontier index)
   double *total, *nsum, *leaf_mean, *best_score, *best_cut, *dist;
@@ -677,3 +679,12 @@ void launch_level_best(et_ctx *ctx, const P &p, int32_t count, BestBufs &bb, int
   k_best_finish<TASK><<<(unsigned)count, BEST_CTA, 0, st>>>(p, s, count);
   ctx->launches++;
 }
+
+BestBufs *best_bufs_create() { return new BestBufs(); }
+void best_bufs_destroy(BestBufs *bb) { delete bb; }
+
+template void launch_level_best<TASK_CLS>(et_ctx *, const P &, int32_t, BestBufs &, int64_t);
+template void launch_level_best<TASK_CLSW>(et_ctx *, const P &, int32_t, BestBufs &, int64_t);
+template void launch_level_best<TASK_REG>(et_ctx *, const P &, int32_t, BestBufs &, int64_t);
+
+}  // namespace etb

@@ -13,7 +13,7 @@
 
 #include "../../include/etgpu.h"
 
-#define ET_ABI_VERSION 1
+#define ET_ABI_VERSION 2
 
 // ---- error plumbing -------------------------------------------------------------------------
 void et_set_error(const char *fmt, ...);

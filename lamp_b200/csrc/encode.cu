@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) k_col_encode(const double *__restrict__ X
 }
 
 
-// Row-major copies for the resident subtree builder (subtree.cuh): 32 x 32 tiles through shared memory.
+// Row-major copy of the byte codes (gathered by k_lane): 32 x 32 tiles through shared memory.
 template <typename T>
 __global__ void __launch_bounds__(256) k_to_rowmajor(const T *__restrict__ src, int64_t ld_src, int64_t n, int32_t d,
                                                      T *__restrict__ dst, int64_t ld_dst) {
@@ -183,17 +183,15 @@ void et_data_drop_rowmajor(et_data *D) {
   D->r8_bytes = D->xr_bytes = 0;
 }
 
-// Builds the row-major copy the resident subtree builder stages rows from (byte codes if the table is coded,
-// else FP64).  A failed allocation just leaves the copy absent: the builder then keeps gathering.
+// Builds the row-major copy k_lane gathers from (byte codes if the table is coded; the FP64 one only on request,
+// ETGPU_ROWMAJOR_FP64=1).  A failed allocation just leaves the copy absent: the kernels then gather by column.
 void et_data_rowmajor(et_ctx *ctx, et_data *D) {
   if (D->n <= 0 || D->d <= 0 || D->coded == 0) return;
-  // byte-coded tables always get the row-major copy (k_lane gathers from it); the FP64 one only serves the opt-in
-  // subtree builder (build.cu)
-  const char *env = getenv("ETGPU_SUB_NCLS");
-  const bool sub_on = env && atoi(env) > 0;
-  if (D->coded != 1 && !sub_on) return;
+  const char *env = getenv("ETGPU_ROWMAJOR_FP64");
+  const bool fp64_on = env && atoi(env) > 0;
+  if (D->coded != 1 && !fp64_on) return;
   if (const char *e2 = getenv("ETGPU_NO_ROWMAJOR"))
-    if (atoi(e2) != 0 && !sub_on) return;
+    if (atoi(e2) != 0) return;
   cudaStream_t st = ctx->stream;
   dim3 block(32, 8), grid((unsigned)ceil_div(D->n, 32), (unsigned)ceil_div(D->d, 32));
   if (D->coded == 1 && !D->r8) {
@@ -222,9 +220,6 @@ void et_data_rowmajor(et_ctx *ctx, et_data *D) {
     ctx->launches++;
   }
 }
-
-namespace {
-}  // namespace
 
 void et_data_drop_codes(et_data *D) {
   et_data_drop_rowmajor(D);

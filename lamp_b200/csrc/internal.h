@@ -21,13 +21,18 @@ struct et_ctx {
   };
   std::vector<Block> cache;
   size_t cache_bytes = 0;
-  static constexpr int N_SIDE = 12;
+  static constexpr int N_SIDE = 8;
   cudaStream_t side[N_SIDE] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[N_SIDE] = {};
-  // resident-subtree kernels: one low-priority stream per (team class, frontier ring slot), so the kernels of
-  // successive levels overlap instead of queueing behind each other's longest subtree
-  static constexpr int N_SUB_CLS = 5, N_SUB_RING = 4;
-  cudaStream_t sub_stream[N_SUB_CLS][N_SUB_RING] = {};
+  // multi-GPU (dist.cu): communicator of this GPU (ncclComm_t), its rank, a stream for collectives that overlap
+  // with kernels, and -- on the front context returned by et_init_multi -- one child context per GPU
+  void *comm = nullptr;
+  int world = 1, rank = 0;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_comm = nullptr;
+  double comm_ms = 0.0;
+  std::vector<et_ctx *> peers;
+  bool is_multi() const { return !peers.empty(); }
 };
 void et_workspace_free(Workspace *ws);
 // api.cu: device blocks through the context's cache (null on failure, like cudaMalloc != cudaSuccess)
@@ -47,8 +52,8 @@ struct et_data {
   uint8_t *coff = nullptr; // [d] 0 if the column holds a NaN, else 1
   int64_t ldc = 0;         // code column stride in bytes (n rounded up to 128)
   double *dict = nullptr;  // [d][256] ascending distinct values, padded with +inf
-  // row-major copies for the resident subtree builder (subtree.cuh): byte codes [n][rs8] when the table is coded,
-  // else FP64 [n][rsd]; rows are 16-byte multiples so a row moves with full vector loads
+  // row-major copies gathered by the lane-per-candidate kernel (k_lane): byte codes [n][rs8] when the table is
+  // coded, else FP64 [n][rsd]; rows are 16-byte multiples so a row moves with full vector loads
   uint8_t *r8 = nullptr;
   int64_t rs8 = 0;   // bytes per coded row
   double *xr = nullptr;
@@ -60,6 +65,7 @@ struct et_data {
   double *y_reg = nullptr;
   double *w = nullptr;
   std::vector<int64_t> root_hist;  // class counts of the whole table
+  std::vector<et_data *> shards;   // multi-GPU front handle: the replica on every GPU (nothing else is set)
 };
 
 // Device forest node: all trees concatenated in pre-order, one 16-byte node fetched with a single
@@ -80,12 +86,19 @@ struct et_forest {
   int32_t is_regression = 0;
   int32_t m = 0;
   int64_t total_nodes = 0, total_leaves = 0;
+  int32_t d_min = 0;  // features a sample row must have: 1 + the largest split feature (the training d after a build)
   std::vector<int64_t> tree_off;  // m + 1, node offsets (host copy)
   // device-resident forest (what predict traverses)
   int64_t *d_tree_off = nullptr;  // m + 1
   PNode *d_nodes = nullptr;       // total_nodes
   double *d_leaf = nullptr;       // total_leaves x leaf_width
   size_t nodes_bytes = 0, leaf_bytes = 0;  // allocation sizes when the blocks came from et_dev_alloc (else 0)
+  // multi-GPU: sort key of every tree when shards are gathered (global tree id / position in the call's forest)
+  std::vector<int64_t> order_key;
+  // multi-GPU front handle: the per-GPU forests of the trees each GPU built, and the gathered whole forest (on the
+  // first GPU) that the export calls read
+  std::vector<et_forest *> shards;
+  et_forest *full = nullptr;
   // lazily fetched host copy (export)
   bool host_ready = false;
   std::vector<PNode> h_nodes;
@@ -100,13 +113,14 @@ struct BuildArgs {
   int64_t seed;
   const int32_t *tree_ids;
   const et_replay *replay;
+  const int64_t *order_keys = nullptr;  // gather order of the trees (default: the global tree ids)
 };
 
 // encode.cu
 static inline size_t et_coff_bytes(int32_t d) { return ((size_t)d + 15) / 16 * 16 + 16; }
 void et_data_encode(et_ctx *ctx, et_data *data);
 void et_data_drop_codes(et_data *data);  // gives the coded copy back to the context's block cache
-void et_data_rowmajor(et_ctx *ctx, et_data *data);  // row-major copy for the resident subtree builder
+void et_data_rowmajor(et_ctx *ctx, et_data *data);  // row-major copy gathered by k_lane
 void et_data_drop_rowmajor(et_data *data);
 // build.cu
 void et_build_forest(et_ctx *ctx, et_data *data, const BuildArgs &a, et_forest *out, et_stats *stats);
@@ -114,5 +128,16 @@ void et_build_forest(et_ctx *ctx, et_data *data, const BuildArgs &a, et_forest *
 void et_predict_device_impl(et_ctx *ctx, et_forest *f, const double *x_dev, int64_t n, int32_t d,
                             double *out_dev, int sum_only);
 // api.cu
+et_data *et_data_alloc_internal(et_ctx *ctx, int64_t n, int32_t d);
+void et_predict_host_impl(et_ctx *ctx, et_forest *f, const double *x, int64_t n, int32_t d, double *out, int sum_only,
+                          int want_regression);
+// dist.cu: the multi-GPU front context (et_init_multi) behind the ordinary calls
+void et_multi_shutdown(et_ctx *front);
+void et_multi_replicate(et_ctx *front, et_data *front_data);  // shards[0] is filled: broadcast it to the other GPUs
+void et_multi_broadcast_columns(et_ctx *front, et_data *front_data, int32_t first_col, int32_t n_cols);
+void et_multi_build(et_ctx *front, et_data *D, const BuildArgs &a, int leaf_width, int is_regression, et_forest **out,
+                    et_stats *stats);
+void et_multi_predict(et_ctx *front, et_forest *f, const double *x, int64_t n, int32_t d, double *out, int sum_only,
+                      int want_regression);
 void et_launch_transpose(et_ctx *ctx, const double *src_rowmajor, int64_t rows, int32_t d,
                          double *dst_colmajor, int64_t ld, int64_t row0);

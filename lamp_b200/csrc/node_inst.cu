@@ -1,0 +1,145 @@
+// node_inst.cu -- instantiates the node kernels (node.cuh) for ONE task and launches a level of them.
+// Compiled three times (-DET_TASK=0 unweighted classification, 1 weighted classification, 2 regression): the
+// kernels are large, so each task is its own object and the three compile side by side.
+#include "node.cuh"
+
+#ifndef ET_TASK
+#error "compile with -DET_TASK=0|1|2"
+#endif
+
+namespace etb {
+
+namespace {
+
+template <int TASK, typename VT>
+void launch_lane(et_ctx *ctx, const P &p, int32_t count, int qi, int NW, size_t smem_per_warp, cudaStream_t st) {
+  const unsigned grid = (unsigned)ceil_div(count, LANE_WARPS);
+  if (NW <= 2)
+    k_lane<TASK, VT, true><<<grid, 32 * LANE_WARPS, smem_per_warp * LANE_WARPS, st>>>(p, count, qi, NW);
+  else
+    k_lane<TASK, VT, false><<<grid, 32 * LANE_WARPS, smem_per_warp * LANE_WARPS, st>>>(p, count, qi, NW);
+  ctx->launches++;
+}
+
+// the byte-coded CTA teams exist for unweighted classification only
+template <int TASK, int TEAM>
+void launch_coded_team(const P &p, int32_t count, int qi, size_t smem, cudaStream_t st) {
+  if constexpr (TASK == TASK_CLS) k_node<TASK_CLS, TEAM, true><<<(unsigned)count, TEAM, smem, st>>>(p, count, qi);
+}
+
+template <int TASK>
+void set_coded_team_attr(const LevelCfg &lc) {
+  if constexpr (TASK == TASK_CLS) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK_CLS, MID_TEAM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)lc.smem_mid));
+    CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK_CLS, CBIG_TEAM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)lc.smem_cta));
+  }
+}
+
+}  // namespace
+
+// One level = one launch per non-empty size class.  The classes are independent (disjoint nodes), so each runs
+// on its own stream: the few long-running CTAs of the large nodes overlap with the many small teams instead of
+// serialising behind them.  The chunked path of the wide nodes is a sequence of kernels with host round trips
+// (candidate rounds); it runs on the main stream after the other classes have been queued on theirs.
+// (ETGPU_TIMING serialises the classes to time each.)
+template <>
+void launch_level<ET_TASK>(et_ctx *ctx, const P &p, const int32_t *qn, int64_t wide_rows, const LevelCfg &lc,
+                           PhaseTimer &pt, EventTimer &et, WideBufs *wb) {
+  constexpr int TASK = ET_TASK;
+  cudaStream_t main_st = ctx->stream;
+  const bool fork = !pt.on;
+  const bool has_wide = qn[Q_WIDE] > 0;
+  int used = 0;
+  for (int q = 0; q < NQ; q++) used += (qn[q] > 0);
+  const int e0 = et.rec(main_st);
+  if (fork && used > 1) cudaEventRecord(ctx->ev_fork, main_st);
+  bool joined[NQ] = {false};
+  int first = has_wide ? 0 : 1;  // the main stream belongs to the wide nodes when there are any
+  auto stream_for = [&](int side) -> cudaStream_t {
+    if (!fork || used <= 1 || first) {  // else the first (largest) class stays on the main stream
+      first = 0;
+      return main_st;
+    }
+    cudaStreamWaitEvent(ctx->side[side], ctx->ev_fork, 0);
+    joined[side] = true;
+    return ctx->side[side];
+  };
+  // largest teams first: their CTAs run longest
+  if (qn[Q_CTA] > 0) {
+    pt.start();
+    cudaStream_t st = stream_for(Q_CTA);
+    if (lc.coded_big)
+      launch_coded_team<TASK, CBIG_TEAM>(p, qn[Q_CTA], Q_CTA, lc.smem_cta, st);
+    else
+      k_node<TASK, CTA_TEAM, false><<<(unsigned)qn[Q_CTA], CTA_TEAM, lc.smem_cta, st>>>(p, qn[Q_CTA], Q_CTA);
+    ctx->launches++;
+    pt.stop(PhaseTimer::CTA);
+  }
+  if (qn[Q_MID] > 0) {
+    pt.start();
+    cudaStream_t st = stream_for(Q_MID);
+    if (lc.coded_big)
+      launch_coded_team<TASK, MID_TEAM>(p, qn[Q_MID], Q_MID, lc.smem_mid, st);
+    else
+      k_node<TASK, MID_TEAM, false><<<(unsigned)qn[Q_MID], MID_TEAM, lc.smem_mid, st>>>(p, qn[Q_MID], Q_MID);
+    ctx->launches++;
+    pt.stop(PhaseTimer::MID);
+  }
+  for (int q = Q_WARP; q >= 0; q--) {
+    if (qn[q] <= 0) continue;
+    pt.start();
+    cudaStream_t st = stream_for(q);
+    if (lc.coded) {
+      launch_lane<TASK, uint8_t>(ctx, p, qn[q], q, 1 << q, lc.smem_lane[q], st);
+    } else if (q == Q_LANE0) {
+      launch_lane<TASK, double>(ctx, p, qn[q], q, 1, lc.smem_lane[0], st);
+    } else {  // FP64 tables: only class Q_WARP is populated besides class Q_LANE0
+      k_node<TASK, 32, false>
+          <<<(unsigned)ceil_div(qn[q], WARPS_PER_CTA), 32 * WARPS_PER_CTA, lc.smem_warp * WARPS_PER_CTA, st>>>(p, qn[q], q);
+      ctx->launches++;
+    }
+    pt.stop(PhaseTimer::LANE);
+  }
+  if (has_wide) {
+    pt.start();
+    if constexpr (TASK != TASK_CLSW) wide_level<TASK>(ctx, p, qn[Q_WIDE], wide_rows, lc, *wb, main_st);
+    pt.stop(PhaseTimer::WIDE);
+  }
+  for (int i = 0; i < NQ; i++) {
+    if (joined[i]) {
+      cudaEventRecord(ctx->ev_join[i], ctx->side[i]);
+      cudaStreamWaitEvent(main_st, ctx->ev_join[i], 0);
+    }
+  }
+  const int e1 = et.rec(main_st);
+  et.spans[0].push_back({e0, e1});
+  if (qn[Q_MID] + qn[Q_CTA] + qn[Q_WIDE] > 0) et.spans[1].push_back({e0, e1});
+}
+
+template <>
+void set_smem_attr<ET_TASK>(const LevelCfg &lc) {
+  constexpr int TASK = ET_TASK;
+  if (lc.coded_big) {
+    set_coded_team_attr<TASK>(lc);
+  } else {
+    CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, MID_TEAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)lc.smem_mid));
+    CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, CTA_TEAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)lc.smem_cta));
+  }
+  if (lc.coded) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(std::max(lc.smem_lane[0], lc.smem_lane[1]) * LANE_WARPS)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(std::max(lc.smem_lane[2], std::max(lc.smem_lane[3], lc.smem_lane[4])) * LANE_WARPS)));
+  } else {
+    CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(lc.smem_lane[0] * LANE_WARPS)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_node<TASK, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(lc.smem_warp * WARPS_PER_CTA)));
+  }
+}
+
+}  // namespace etb

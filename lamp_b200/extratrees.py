@@ -122,13 +122,37 @@ def adt_to_flat(root, leaf_width: int) -> FlatTree:
 
 
 class Context:
-    """One GPU.  The reference hides its thread pool behind the call; so does this (default context)."""
+    """One GPU, or -- Context.multi(devices) -- several GPUs of one box behind one handle (et_init_multi: trees
+    sharded by tree id, NCCL inside the library).  The reference hides its thread pool behind the call
+    (pkg:653-675); so does this (default context)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _handle=None, _devices=None):
+        if _handle is None:
+            h = C.c_void_p()
+            check(capi.lib().et_init(device, C.byref(h)))
+            _handle, _devices = h, [device]
+        self.h = _handle
+        self.device = _devices[0]
+        self.devices = list(_devices)
+
+    @classmethod
+    def multi(cls, devices) -> "Context":
+        devs = np.ascontiguousarray(list(devices), dtype=np.int32)
         h = C.c_void_p()
-        check(capi.lib().et_init(device, C.byref(h)))
-        self.h = h
-        self.device = device
+        check(capi.lib().et_init_multi(ptr(devs, ip), len(devs), C.byref(h)))
+        return cls(_handle=h, _devices=devs.tolist())
+
+    @property
+    def n_devices(self) -> int:
+        return len(self.devices)
+
+    def comm_init_rank(self, world: int, rank: int, unique_id: bytes):
+        """One process per GPU: attach an NCCL communicator (the launcher distributes rank 0's unique id)."""
+        buf = (C.c_uint8 * capi.COMM_ID_BYTES).from_buffer_copy(unique_id)
+        check(capi.lib().et_comm_init_rank(self.h, world, rank, buf))
+
+    def comm_last_ms(self) -> float:
+        return float(capi.lib().et_comm_last_ms(self.h))
 
     def set_stream(self, cuda_stream: Optional[int]):
         check(capi.lib().et_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))

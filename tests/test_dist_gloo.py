@@ -1,16 +1,15 @@
-"""Host-side logic of the multi-GPU path on CPU: world_size-2 gloo run of tree sharding, the all-gather
-of serialized trees and the vote all-reduce (lamp_b200/dist.py).  Compute is injected from the oracle."""
+"""Host-side logic of the one-process-per-GPU path on CPU: a world_size-2 gloo run of the tree sharding and of the
+NCCL unique-id hand-off (lamp_b200/dist.py).  The collectives themselves run inside libetgpu.so on device buffers
+(dist.cu) and are covered by the GPU tests (single-device group) and scripts/dist_check.py (2+ GPUs)."""
 import os
 import socket
 
 import numpy as np
 import pytest
-import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from lamp_b200 import dist as D
-from oracle import oracle as O
 
 
 def _free_port():
@@ -21,43 +20,34 @@ def _free_port():
     return p
 
 
-def _serialize(trees, lw, regression):
-    return dict(tree_sizes=np.array([t.n_nodes for t in trees], np.int32),
-                feature=np.concatenate([t.feature for t in trees]), cut=np.concatenate([t.cut for t in trees]),
-                mil=np.concatenate([t.mil for t in trees]), left=np.concatenate([t.left for t in trees]),
-                right=np.concatenate([t.right for t in trees]),
-                leaf=np.concatenate([t.leaf for t in trees]).reshape(-1, lw), leaf_width=lw, regression=regression)
-
-
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        rng = np.random.default_rng(0)
-        x = rng.normal(size=(400, 6))
-        y = (x[:, 0] + x[:, 1] > 0).astype(np.int32)
         m = 7
-        full = O.build_forest_classification(x, y, None, 2, 2, 3, m, 4, seed=5)  # identical on every rank
-        trees = full.trees()
+        # every rank builds its own shard: the shards partition 0..m-1 and keep tree-id order inside a rank
+        local, ids = D.build_forest_sharded(lambda tid: [int(t) * 10 for t in tid], m)
+        assert ids.tolist() == list(range(rank, m, world)) and local == [t * 10 for t in ids]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, ids.tolist())
+        assert sorted(sum(gathered, [])) == list(range(m))
+        # the NCCL unique id is made on rank 0 only and arrives unchanged everywhere
+        made = []
 
-        def build(ids):  # stands in for the GPU build of this rank's shard
-            return [trees[t] for t in ids]
+        def make_id():
+            made.append(1)
+            return bytes((7 * i + 3) % 256 for i in range(128))
 
-        local, ids = D.build_forest_sharded(build, m)
-        assert ids.tolist() == list(range(rank, m, world))
-        merged = D.gather_forest(_serialize(local, 2, False), ids)
-        ref = _serialize(trees, 2, False)
-        for k in ("tree_sizes", "feature", "mil", "left", "right"):
-            assert np.array_equal(merged[k], ref[k]), k
-        assert np.array_equal(merged["cut"].view(np.int64), ref["cut"].view(np.int64))
-        assert np.array_equal(merged["leaf"], ref["leaf"])
-        # sharded predict: per-rank partial sums -> all-reduce -> / m
-        part = np.zeros((len(x), 2))
-        for t in local:
-            part += O.import_forest([t], False).predict(x)
-        pred = D.predict_sharded(part, m)
-        np.testing.assert_allclose(pred, full.predict(x), rtol=1e-12, atol=0)
+        uid = D.exchange_unique_id(make_id)
+        assert uid == bytes((7 * i + 3) % 256 for i in range(128))
+        assert len(made) == (1 if rank == 0 else 0)
+        # a malformed id is refused on every rank
+        try:
+            D.exchange_unique_id(lambda: b"short")
+            raise AssertionError("short id accepted")
+        except RuntimeError:
+            pass
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))

@@ -14,14 +14,14 @@ pytestmark = pytest.mark.gpu
 NAN = float("nan")
 
 
-@pytest.fixture(autouse=True, params=["codes", "fp64", "codes-subtrees", "fp64-subtrees"])
+@pytest.fixture(autouse=True, params=["codes", "fp64", "codes-onecta", "fp64-onecta"])
 def table_coding(request, monkeypatch):
     """Every test runs with the byte-coded copy of the table (encode.cu; used whenever all columns have <= 255
-    distinct values) and with FP64 gathers only (ETGPU_NO_CODES=1), each with the level-wise kernels alone and
-    with the opt-in resident subtree builder (subtree.cuh, ETGPU_SUB_NCLS=5: nodes of up to ~200 rows are built
-    to the leaves out of shared memory, asynchronously to the level loop)."""
+    distinct values) and with FP64 gathers only (ETGPU_NO_CODES=1), each with nodes of more than 2048 rows cut into
+    chunks of rows over several CTAs (wide.cu, the default) and with one CTA per node whatever its size
+    (ETGPU_WIDE_MIN beyond any table)."""
     monkeypatch.setenv("ETGPU_NO_CODES", "1" if request.param.startswith("fp64") else "0")
-    monkeypatch.setenv("ETGPU_SUB_NCLS", "5" if request.param.endswith("subtrees") else "0")
+    monkeypatch.setenv("ETGPU_WIDE_MIN", "2147483647" if request.param.endswith("onecta") else "2048")
     return request.param
 
 
@@ -434,3 +434,74 @@ def test_full_size_regression_properties():
     assert f.stats["parallel_sum_nodes"] > 0
     pred = et.predictRegression(f, x[:50_000])
     assert np.mean((pred - y[:50_000]) ** 2) < 0.2 * np.var(y)
+
+
+# ---- nodes cut into row chunks over several CTAs (wide.cu) -----------------------------------------------------
+@pytest.mark.parametrize("chunk", [1024, 2048, 8192])
+def test_wide_nodes_replay_small_chunks(mnist, chunk, monkeypatch, table_coding):
+    """Small chunks force many chunks per node on a small table: replay stays bit-exact (classification: integer
+    histograms merged with atomics; the stable partition places a chunk after the chunks before it)."""
+    if table_coding.endswith("onecta"):
+        pytest.skip("chunked path switched off in this variant")
+    monkeypatch.setenv("ETGPU_WIDE_CHUNK", str(chunk))
+    x, y = mnist
+    of = O.build_forest_classification(x, y, None, 10, 2, 28, 2, 2, seed=17, record_trace=True)
+    gf = et.buildForestClassification(x, y, None, 10, 2, 28, 2, 2, seed=17, replay=oracle_replay(of))
+    assert_trees_bit_exact(gf, of)
+    assert gf.stats["replay_mismatches"] == 0
+    xs, ys = synth_classification(9000, 12, 3, 5, nan_frac=0.1, const_cols=2, quantize=2)
+    of = O.build_forest_classification(xs, ys, None, 3, 2, 4, 3, 2, seed=2, record_trace=True)
+    gf = et.buildForestClassification(xs, ys, None, 3, 2, 4, 3, 2, seed=2, replay=oracle_replay(of))
+    assert_trees_bit_exact(gf, of)
+    xr, yr = synth_regression(9000, 10, 4, nan_frac=0.05)
+    of = O.build_forest_regression(xr, yr, 5, 3, 3, 2, seed=3, record_trace=True)
+    gf = et.buildForestRegression(xr, yr, 5, 3, 3, 2, seed=3, replay=oracle_replay(of))
+    assert_trees_bit_exact(gf, of)
+    assert gf.stats["ambiguous_splits"] == 0
+
+
+def test_wide_and_one_cta_paths_build_the_same_free_running_forest(mnist, monkeypatch):
+    """The chunked path draws the same candidates as the one-CTA path, and unweighted classification scores are
+    exact in both: a free-running forest does not depend on which path built a node."""
+    x, y = mnist
+    monkeypatch.setenv("ETGPU_WIDE_MIN", "2048")
+    a = et.buildForestClassification(x, y, None, 10, 2, 28, 3, 4, seed=77)
+    monkeypatch.setenv("ETGPU_WIDE_MIN", "2147483647")
+    b = et.buildForestClassification(x, y, None, 10, 2, 28, 3, 4, seed=77)
+    for t in range(3):
+        fa, fb = a.flat(t), b.flat(t)
+        assert np.array_equal(fa.feature, fb.feature) and np.array_equal(fa.cut.view(np.int64), fb.cut.view(np.int64))
+        assert np.array_equal(fa.leaf, fb.leaf)
+    for key in ("v_mm", "v_sc", "s_rows", "p_rows", "draws", "const_hits", "scored", "nodes"):
+        assert a.stats[key] == b.stats[key], key
+
+
+# ---- argument handling (advisor findings, round 1) ---------------------------------------------------------------
+def test_predict_rejects_samples_narrower_than_the_split_features(mnist):
+    x, y = mnist
+    x, y = x[:800], y[:800]
+    f = et.buildForestClassification(x, y, None, 10, 2, 28, 2, 2, seed=1)
+    used = max(int(f.flat(t).feature.max()) for t in range(2))
+    with pytest.raises(ValueError):  # the reference fails with ArrayIndexOutOfBounds (pkg:517)
+        et.predictClassification(f, x[:10, :used])
+    assert et.predictClassification(f, x[:10, : used + 1]).shape == (10, 10)
+    g = et.Forest.import_packed(f.export_packed())
+    with pytest.raises(ValueError):
+        et.predictClassification(g, x[:10, :used])
+
+
+def test_resident_target_with_per_call_weights(mnist):
+    """weights passed with a resident target are used (not silently dropped), and a call without weights keeps the
+    attached ones."""
+    x, y = mnist
+    x, y = x[:1500], y[:1500]
+    w = np.concatenate([np.ones(750), np.zeros(750)])
+    ref = et.buildForestClassification(x, y, w, 10, 2, 16, 2, 4, seed=9)
+    dd = et.DeviceData.from_rowmajor(x)
+    dd.set_target_classification(y, 10)
+    got = et.buildForestClassification(dd, None, w, 10, 2, 16, 2, 4, seed=9)
+    again = et.buildForestClassification(dd, None, None, 10, 2, 16, 2, 4, seed=9)  # attached weights stay
+    for t in range(2):
+        for other in (got, again):
+            assert np.array_equal(ref.flat(t).feature, other.flat(t).feature)
+            assert np.array_equal(ref.flat(t).leaf, other.flat(t).leaf)
