@@ -118,8 +118,37 @@ extern "C" int et_init(int32_t device, et_ctx **out) {
   ET_API_END
 }
 
+void et_ctx_acquire(et_ctx *ctx) {
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  ctx->live_handles++;
+}
+
+static void ctx_destroy(et_ctx *ctx);
+
+void et_ctx_release(et_ctx *ctx) {
+  bool destroy = false;
+  {
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    ctx->live_handles--;
+    destroy = ctx->shutdown_requested && ctx->live_handles <= 0;
+  }
+  if (destroy) ctx_destroy(ctx);
+}
+
+// With et_data / et_forest handles still alive the teardown is deferred until the last of them is freed.
 extern "C" void et_shutdown(et_ctx *ctx) {
   if (!ctx) return;
+  {
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (ctx->live_handles > 0) {
+      ctx->shutdown_requested = true;
+      return;
+    }
+  }
+  ctx_destroy(ctx);
+}
+
+static void ctx_destroy(et_ctx *ctx) {
   if (ctx->is_multi()) {
     et_multi_shutdown(ctx);
     delete ctx;
@@ -277,6 +306,7 @@ extern "C" int et_data_dense_colblock(et_ctx *ctx, et_data *D, const double *col
     et_multi_broadcast_columns(ctx, D, first_col, n_cols);
     return ET_OK;
   }
+  if (!D->x) ET_FAIL(ET_EINVAL, "et_data_dense_colblock: not a dense table");
   if (first_col < 0 || n_cols < 0 || first_col + n_cols > D->d)
     ET_FAIL(ET_EINVAL, "et_data_dense_colblock: columns [%d,%d) outside [0,%d)", first_col, first_col + n_cols, D->d);
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
@@ -373,6 +403,12 @@ __global__ void k_csc_scatter(const int64_t *__restrict__ colptr, const int32_t 
   x[(int64_t)(c0 + lo) * ld + rowidx[e - e0]] = val[e - e0];
 }
 
+// CSC input (BASELINE configs[3]).  The stored entries of a column are kept in ascending row order without
+// duplicates (a row listed twice keeps the LATER entry; unsorted input is sorted on the host first), so a kernel
+// finds the value of (row, column) by binary search and everything not stored is an implicit 0.0 with dense
+// semantics.  Tables whose dense form is small (ETGPU_CSC_DENSE_MAX bytes, default 4 GiB) are expanded into the
+// resident column-major FP64 matrix instead: one gather per value is cheaper than a search, and such a table can
+// still be byte-coded.  Larger tables stay sparse in HBM: 12 bytes per stored entry.
 extern "C" int et_data_csc(et_ctx *ctx, const int64_t *colptr, const int32_t *rowidx, const double *val, int64_t n,
                            int32_t d, et_data **out) {
   ET_API_BEGIN
@@ -385,15 +421,79 @@ extern "C" int et_data_csc(et_ctx *ctx, const int64_t *colptr, const int32_t *ro
     return ET_OK;
   }
   if (n < 0 || d < 0) ET_FAIL(ET_EINVAL, "negative table dimensions");
+  if (n > 0x7fffffff) ET_FAIL(ET_EUNSUPPORTED, "tables with more than 2^31-1 rows are not supported");
   if (colptr[0] != 0) ET_FAIL(ET_EINVAL, "et_data_csc: colptr[0] must be 0");
   for (int32_t c = 0; c < d; c++)
     if (colptr[c + 1] < colptr[c]) ET_FAIL(ET_EINVAL, "et_data_csc: colptr decreases at column %d", c);
-  const int64_t nnz = colptr[d];
+  int64_t nnz = colptr[d];
   if (nnz > 0 && (!rowidx || !val)) ET_FAIL(ET_EINVAL, "et_data_csc: NULL argument");
-  for (int64_t e = 0; e < nnz; e++)
-    if (rowidx[e] < 0 || rowidx[e] >= n) ET_FAIL(ET_EINVAL, "et_data_csc: row index %d outside [0,%lld)", rowidx[e], (long long)n);
+  bool clean = true;  // ascending rows without duplicates inside every column
+  for (int32_t c = 0; c < d; c++) {
+    for (int64_t e = colptr[c]; e < colptr[c + 1]; e++) {
+      if (rowidx[e] < 0 || rowidx[e] >= n)
+        ET_FAIL(ET_EINVAL, "et_data_csc: row index %d outside [0,%lld)", rowidx[e], (long long)n);
+      if (e > colptr[c] && rowidx[e] <= rowidx[e - 1]) clean = false;
+    }
+  }
+  // unsorted columns / duplicate rows: a cleaned copy (stable sort by row; of equal rows the last one stays)
+  std::vector<int64_t> cp2;
+  std::vector<int32_t> row2;
+  std::vector<double> val2;
+  if (!clean) {
+    cp2.assign((size_t)d + 1, 0);
+    row2.reserve((size_t)nnz);
+    val2.reserve((size_t)nnz);
+    std::vector<int64_t> ord;
+    for (int32_t c = 0; c < d; c++) {
+      const int64_t a = colptr[c], b = colptr[c + 1];
+      ord.resize((size_t)(b - a));
+      for (int64_t e = a; e < b; e++) ord[(size_t)(e - a)] = e;
+      std::stable_sort(ord.begin(), ord.end(), [&](int64_t x, int64_t y) { return rowidx[x] < rowidx[y]; });
+      for (size_t q = 0; q < ord.size(); q++) {
+        if (q + 1 < ord.size() && rowidx[ord[q + 1]] == rowidx[ord[q]]) continue;  // a later entry of the same row follows
+        row2.push_back(rowidx[ord[q]]);
+        val2.push_back(val[ord[q]]);
+      }
+      cp2[(size_t)c + 1] = (int64_t)row2.size();
+    }
+    colptr = cp2.data();
+    rowidx = row2.data();
+    val = val2.data();
+    nnz = colptr[d];
+  }
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CUDA_CHECK(cudaSetDevice(ctx->device));
+  size_t dense_max = (size_t)4 << 30;
+  if (const char *env = getenv("ETGPU_CSC_DENSE_MAX")) dense_max = (size_t)atoll(env);
+  const bool expand = (size_t)n * (size_t)std::max(d, 1) * sizeof(double) <= dense_max;
+  if (!expand) {
+    // ---- the table stays sparse in HBM
+    std::unique_ptr<et_data> D(new et_data());
+    D->ctx = ctx;
+    D->n = n;
+    D->d = d;
+    D->ld = ((n + 15) / 16) * 16;
+    D->coded = -1;
+    D->csc_nnz = nnz;
+    try {
+      CUDA_CHECK(cudaMalloc((void **)&D->csc_colptr, ((size_t)d + 1) * sizeof(int64_t)));
+      CUDA_CHECK(cudaMalloc((void **)&D->csc_row, std::max<size_t>(1, (size_t)nnz) * sizeof(int32_t)));
+      CUDA_CHECK(cudaMalloc((void **)&D->csc_val, std::max<size_t>(1, (size_t)nnz) * sizeof(double)));
+      CUDA_CHECK(cudaMemcpyAsync(D->csc_colptr, colptr, ((size_t)d + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+      if (nnz > 0) {
+        CUDA_CHECK(cudaMemcpyAsync(D->csc_row, rowidx, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(D->csc_val, val, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      }
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    } catch (...) {
+      cudaFree(D->csc_colptr);
+      cudaFree(D->csc_row);
+      cudaFree(D->csc_val);
+      throw;
+    }
+    *out = D.release();
+    return ET_OK;
+  }
   et_data *D = data_alloc(ctx, n, d);
   int64_t *d_colptr = nullptr;
   int32_t *d_row = nullptr;
@@ -548,14 +648,19 @@ extern "C" void et_data_free(et_data *D) {
     return;
   }
   if (D->ctx) cudaSetDevice(D->ctx->device);
-  std::unique_lock<std::recursive_mutex> lk;
-  if (D->ctx) lk = std::unique_lock<std::recursive_mutex>(D->ctx->mu);
-  et_dev_free(D->ctx, D->x, D->x_bytes);
-  et_data_drop_codes(D);
-  if (D->y_cls) cudaFree(D->y_cls);
-  if (D->y_reg) cudaFree(D->y_reg);
-  if (D->w) cudaFree(D->w);
-  delete D;
+  {
+    std::unique_lock<std::recursive_mutex> lk;
+    if (D->ctx) lk = std::unique_lock<std::recursive_mutex>(D->ctx->mu);
+    et_dev_free(D->ctx, D->x, D->x_bytes);
+    et_data_drop_codes(D);
+    if (D->csc_colptr) cudaFree(D->csc_colptr);
+    if (D->csc_row) cudaFree(D->csc_row);
+    if (D->csc_val) cudaFree(D->csc_val);
+    if (D->y_cls) cudaFree(D->y_cls);
+    if (D->y_reg) cudaFree(D->y_reg);
+    if (D->w) cudaFree(D->w);
+  }
+  delete D;  // (outside the lock: releasing the last handle may run the context's deferred shutdown)
 }
 
 // ---- build ----------------------------------------------------------------------------------

@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(BEST_CTA) k_best_eval(P p, BestState s, const 
   const int32_t tree = p.cur.tree[i], b = p.cur.begin[i], n = p.cur.end[i] - b;
   const int64_t base = (int64_t)tree * p.n + b;
   const int32_t *idx = p.idx_src + base;
-  const double *col = p.X + (int64_t)f * p.ld;
+  const Col col = col_of(p, f);
   // ---- minmax / hasMissing (pkg:34-54) and the NaN rows per class
   if (tid == 0) {
     sh_nan = 0;
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(BEST_CTA) k_best_eval(P p, BestState s, const 
   double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;
   int nn = 0;
   for (int32_t j = tid; j < n; j += BEST_CTA) {
-    const double x = col[idx[j]];
+    const double x = col_at(col, idx[j]);
     if (x < mn) mn = x;
     if (x > mx) mx = x;
     if (x != x) {
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(BEST_CTA) k_best_eval(P p, BestState s, const 
   // ---- this thread's cutpoint
   const int32_t ii = it.chunk * BEST_CTA + tid;
   const bool active = ii < n;
-  const double cut = active ? col[idx[ii]] : 0.0;
+  const double cut = active ? col_at(col, idx[ii]) : 0.0;
   const double G = s.total[i];
   double s_not = NAN, s_mil = NAN;
   // streams the node through shared memory; `body(j)` sees xs[j], ys[j], cs[j] of every position in subset order
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(BEST_CTA) k_best_eval(P p, BestState s, const 
       const int32_t tn2 = min(BEST_TILE, n - t0);
       __syncthreads();
       for (int32_t j = tid; j < tn2; j += BEST_CTA) {
-        xs[j] = col[idx[t0 + j]];
+        xs[j] = col_at(col, idx[t0 + j]);
         if (TASK == TASK_REG) ys[j] = p.yr_src[base + t0 + j];
         if (TASK == TASK_CLSW) ys[j] = p.w_src[base + t0 + j];
         if (TASK != TASK_REG) cs[j] = p.yc_src[base + t0 + j];
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(BEST_CTA) k_best_eval(P p, BestState s, const 
     BestRes r;
     r.score = sc;
     r.idx = ix;
-    r.cut = (ix >= 0) ? col[idx[ix]] : NAN;
+    r.cut = (ix >= 0) ? col_at(col, idx[ix]) : NAN;
     r.flags = (ml ? 2 : 0) | (ix >= 0 ? 4 : 0);
     res[blockIdx.x] = r;
   }
@@ -530,9 +530,9 @@ __global__ void __launch_bounds__(BEST_CTA) k_best_finish(P p, BestState s, int3
   }
   // ---- stable partition of the node's rows (pkg:1024-1039 / 841-856)
   const int32_t *idx = p.idx_src + base + b;
-  const double *col = p.X + (int64_t)best_feature * p.ld;
+  const Col col = col_of(p, best_feature);
   auto goes_left = [&](int32_t j) {
-    const double x = col[idx[j]];
+    const double x = col_at(col, idx[j]);
     return (x < best_cut) || (best_mil && (x != x));
   };
   int32_t cnt = 0;

@@ -239,7 +239,11 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
   auto wide_min_for = [&](int64_t big_rows) -> int32_t {
     if (!lc.wide) return 0x7fffffff;
     if (wide_min_fixed >= 0) return (int32_t)wide_min_fixed;
-    return (int32_t)std::min<int64_t>(0x7fffffff, std::max<int64_t>(NM_MAX, big_rows / (2 * cta_slots)));
+    // (and never below a size one CTA finishes faster than the chunked path's fixed cost of ~0.3 ms per level).
+    // Regression: the one-CTA team of a large node holds an SM alone (512 threads, moment sums), the chunked path
+    // was measured faster at every level of the 1M-row table, so it takes every node above NM_MAX rows.
+    if (task == TASK_REG) return NM_MAX;
+    return (int32_t)std::min<int64_t>(0x7fffffff, std::max<int64_t>(16384, big_rows / (4 * cta_slots)));
   };
   if (task == TASK_CLS)
     set_smem_attr<TASK_CLS>(lc);
@@ -265,6 +269,10 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
   size_t per_sample = 2 * (4 + (task == TASK_REG ? 8 : 4) + (task == TASK_CLSW ? 8 : 0));
   int64_t max_samples = (int64_t)(((size_t)8 << 30) / per_sample);
   int32_t B = (int32_t)std::max<int64_t>(1, std::min<int64_t>(a.m, max_samples / std::max<int64_t>(n, 1)));
+  if (!replay) {  // ... and the known-constant feature masks of the open nodes (W words per node, two levels) to ~16 GB
+    const int64_t mask_per_tree = std::max<int64_t>(1, n / 4) * (int64_t)W * 8;
+    B = (int32_t)std::max<int64_t>(1, std::min<int64_t>(B, ((int64_t)16 << 30) / mask_per_tree));
+  }
   if (const char *env = getenv("ETGPU_BATCH_TREES")) B = std::max(1, std::min(a.m, atoi(env)));
 
   ws.cnt.ensure(1);
@@ -373,6 +381,9 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       if (const char *env = getenv("ETGPU_NC_MAX")) p.nc_max = std::max(0, atoi(env));
       p.XR = D->xr;
       p.xr_stride = (int32_t)D->rsd;
+      p.csc_colptr = D->csc_colptr;
+      p.csc_row = D->csc_row;
+      p.csc_val = D->csc_val;
       p.tr = trace;
       int srcb = 0, cl = 0;  // cl: frontier slot of the current level
       int32_t F = Bt;

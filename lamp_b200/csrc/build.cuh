@@ -196,7 +196,46 @@ struct P {
   int32_t nc_max;      // k_lane: nodes of up to this many rows draw from their varying-feature set
   const double *XR;    // row-major FP64 [n][xr_stride]
   int32_t xr_stride;
+  // CSC table (X == null): column f holds the entries csc_colptr[f] .. csc_colptr[f + 1] - 1 of (csc_row, csc_val)
+  const int64_t *csc_colptr;
+  const int32_t *csc_row;
+  const double *csc_val;
 };
+
+// Column f of the table: dense FP64 values, or the stored entries of a CSC column (everything not stored is 0.0
+// with dense semantics: the reference has no sparse Mat, a CSC table builds the forest of its dense expansion).
+struct Col {
+  const double *v;      // dense: X + f * ld;  CSC: the column's stored values
+  const int32_t *rows;  // CSC: ascending row ids of the stored entries (null: dense)
+  int32_t nnz;
+};
+__device__ __forceinline__ Col col_of(const P &p, int32_t f) {
+  Col c;
+  if (p.csc_row) {
+    const int64_t a = __ldg(p.csc_colptr + f), e = __ldg(p.csc_colptr + f + 1);
+    c.v = p.csc_val + a;
+    c.rows = p.csc_row + a;
+    c.nnz = (int32_t)(e - a);
+  } else {
+    c.v = p.X + (int64_t)f * p.ld;
+    c.rows = nullptr;
+    c.nnz = 0;
+  }
+  return c;
+}
+// value of row r: one gather, or a binary search among the column's stored rows (a miss is an implicit zero)
+__device__ __forceinline__ double col_at(const Col &c, int32_t r) {
+  if (!c.rows) return __ldg(c.v + r);
+  int lo = 0, hi = c.nnz;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(c.rows + mid) < r)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return (lo < c.nnz && __ldg(c.rows + lo) == r) ? __ldg(c.v + lo) : 0.0;
+}
 
 __host__ __device__ inline int size_class(const P &p, int64_t n) {
   int q = 0;

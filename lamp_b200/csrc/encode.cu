@@ -235,6 +235,10 @@ void et_data_drop_codes(et_data *D) {
 // more than 256 distinct values (the builder then gathers FP64 values).
 void et_data_encode(et_ctx *ctx, et_data *D) {
   if (D->coded != 0) return;
+  if (!D->x) {  // CSC table kept sparse: never coded
+    D->coded = -1;
+    return;
+  }
   const char *env = getenv("ETGPU_NO_CODES");
   if ((env && atoi(env) != 0) || D->n <= 0 || D->d <= 0) {
     D->coded = -1;

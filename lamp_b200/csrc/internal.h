@@ -33,6 +33,30 @@ struct et_ctx {
   double comm_ms = 0.0;
   std::vector<et_ctx *> peers;
   bool is_multi() const { return !peers.empty(); }
+  // et_data / et_forest handles still alive on this context: et_shutdown with handles outstanding is deferred until
+  // the last of them is freed (a handle's destructor needs the context's mutex and block cache)
+  int live_handles = 0;
+  bool shutdown_requested = false;
+};
+void et_ctx_acquire(et_ctx *ctx);
+void et_ctx_release(et_ctx *ctx);  // may run the deferred shutdown
+// the context a handle lives on: counted, so the context outlives the handle
+struct CtxHold {
+  et_ctx *p = nullptr;
+  CtxHold() = default;
+  CtxHold(const CtxHold &) = delete;
+  CtxHold &operator=(const CtxHold &) = delete;
+  CtxHold &operator=(et_ctx *c) {
+    if (c) et_ctx_acquire(c);
+    if (p) et_ctx_release(p);
+    p = c;
+    return *this;
+  }
+  operator et_ctx *() const { return p; }
+  et_ctx *operator->() const { return p; }
+  ~CtxHold() {
+    if (p) et_ctx_release(p);
+  }
 };
 void et_workspace_free(Workspace *ws);
 // api.cu: device blocks through the context's cache (null on failure, like cudaMalloc != cudaSuccess)
@@ -40,7 +64,7 @@ void *et_dev_alloc(et_ctx *ctx, size_t bytes);
 void et_dev_free(et_ctx *ctx, void *p, size_t bytes);
 
 struct et_data {
-  et_ctx *ctx = nullptr;
+  CtxHold ctx;
   int64_t n = 0;
   int32_t d = 0;
   int64_t ld = 0;       // column stride in elements (n rounded up to 16)
@@ -59,6 +83,11 @@ struct et_data {
   double *xr = nullptr;
   int64_t rsd = 0;   // doubles per FP64 row
   size_t r8_bytes = 0, xr_bytes = 0;
+  // CSC table kept sparse in HBM (x == null): ascending rows without duplicates inside every column
+  int64_t *csc_colptr = nullptr;  // [d + 1]
+  int32_t *csc_row = nullptr;
+  double *csc_val = nullptr;
+  int64_t csc_nnz = 0;
   // attached targets / weights (resident)
   int32_t *y_cls = nullptr;
   int32_t num_classes = 0;
@@ -81,7 +110,7 @@ struct __align__(16) PNode {
 #define ET_MIL_BIT 0x40000000
 
 struct et_forest {
-  et_ctx *ctx = nullptr;
+  CtxHold ctx;
   int32_t leaf_width = 1;
   int32_t is_regression = 0;
   int32_t m = 0;

@@ -476,11 +476,11 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
         double *scr = s_xs;  // reduction scratch [warp][12] (the value-staging buffer is unused here)
         constexpr int NWP = TEAM / 32;
         for (int g0 = 0; g0 < nb; g0 += 4) {
-          const double *colp[4];
+          Col colp[4];
 #pragma unroll
           for (int c = 0; c < 4; c++) {
             const int32_t f = (g0 + c < nb) ? s_feat[g0 + c] : -1;
-            colp[c] = p.X + (int64_t)(f >= 0 ? f : 0) * p.ld;
+            colp[c] = col_of(p, f >= 0 ? f : 0);
           }
           {
             double mn[4], mx[4];
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
 #pragma unroll
               for (int u2 = 0; u2 < 4; u2++)
 #pragma unroll
-                for (int c = 0; c < 4; c++) x[u2][c] = (r[u2] >= 0) ? __ldg(colp[c] + r[u2]) : 0.0;
+                for (int c = 0; c < 4; c++) x[u2][c] = (r[u2] >= 0) ? col_at(colp[c], r[u2]) : 0.0;
 #pragma unroll
               for (int u2 = 0; u2 < 4; u2++) {
                 if (r[u2] >= 0) {
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
 #pragma unroll
               for (int u2 = 0; u2 < 4; u2++)
 #pragma unroll
-                for (int c = 0; c < 4; c++) x[u2][c] = (r[u2] >= 0) ? __ldg(colp[c] + r[u2]) : 0.0;
+                for (int c = 0; c < 4; c++) x[u2][c] = (r[u2] >= 0) ? col_at(colp[c], r[u2]) : 0.0;
 #pragma unroll
               for (int u2 = 0; u2 < 4; u2++) {
                 const double yd2 = ET_MUL(yd[u2], yd[u2]);
@@ -747,7 +747,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
         const int c = s_ord[oi];
         if (c < 0) break;  // inactive slots sort last
         const int32_t f = s_feat[c];
-        const double *col = p.X + (int64_t)f * p.ld;
+        const Col col = col_of(p, f);
         double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;  // pkg:35-36
         int has_nan = 0;
         if (WARP) {
@@ -756,7 +756,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
           for (int v = 0; v < nv; v++) {
             const int j = v * 32 + lane;
             if (j < n) {
-              const double x = __ldg(col + s_rows[j]);
+              const double x = col_at(col, s_rows[j]);
               s_xs[j] = x;
               if (x < mn) mn = x;
               if (x > mx) mx = x;
@@ -773,7 +773,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
               r4[u2] = (j < n) ? rr[j] : -1;
             }
 #pragma unroll
-            for (int u2 = 0; u2 < 4; u2++) x4[u2] = (r4[u2] >= 0) ? __ldg(col + r4[u2]) : 0.0;
+            for (int u2 = 0; u2 < 4; u2++) x4[u2] = (r4[u2] >= 0) ? col_at(col, r4[u2]) : 0.0;
 #pragma unroll
             for (int u2 = 0; u2 < 4; u2++) {
               if (r4[u2] >= 0) {
@@ -846,7 +846,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
               }
 #pragma unroll
               for (int u2 = 0; u2 < 4; u2++)
-                x4[u2] = (r4[u2] >= 0) ? (staged ? s_xs[r4[u2]] : __ldg(col + r4[u2])) : cut;
+                x4[u2] = (r4[u2] >= 0) ? (staged ? s_xs[r4[u2]] : col_at(col, r4[u2])) : cut;
 #pragma unroll
               for (int u2 = 0; u2 < 4; u2++) {
                 const unsigned long long inc = (x4[u2] < cut) ? 1ull : 0ull;
@@ -874,7 +874,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
               bool lt = false, isn = false;
               int32_t cls = -1;
               if (j < n) {
-                const double x = staged ? s_xs[j] : __ldg(col + rr[j]);
+                const double x = staged ? s_xs[j] : col_at(col, rr[j]);
                 cls = LAB(j);
                 lt = x < cut;
                 isn = x != x;
@@ -896,7 +896,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
             }
           } else {
             for (int32_t j = tid; j < n; j += TEAM) {
-              const double x = staged ? s_xs[j] : __ldg(col + rr[j]);
+              const double x = staged ? s_xs[j] : col_at(col, rr[j]);
               if (x < cut)
                 atomicAdd(&hl[LAB(j)], 1);
               else if (x != x)
@@ -910,7 +910,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
             const int32_t j = j0 + lane;
             bool lt = false, isn = false;
             if (j < n) {
-              const double x = (WARP || staged) ? s_xs[j] : __ldg(col + rr[j]);
+              const double x = (WARP || staged) ? s_xs[j] : col_at(col, rr[j]);
               lt = x < cut;
               isn = x != x;
             }
@@ -1130,7 +1130,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
   }
   // ---- stable partition of the node's segment (pkg:1024-1039)
   {
-    const double *col = p.X + (int64_t)best_feature * p.ld;
+    const Col col = CODED ? Col{nullptr, nullptr, 0} : col_of(p, best_feature);
     const bool mil = best_mil != 0;
     int32_t lpos = b, rpos = b + best_nleft;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -1146,7 +1146,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
           const bool isn = (best_K == 1) && (b8 == 0);
           left = isn ? mil : (((b8 - best_K) & 255) < best_thr);
         } else {
-          const double x = __ldg(col + r);
+          const double x = col_at(col, r);
           left = (x < best_cut) || (mil && (x != x));
         }
       }
@@ -1631,7 +1631,8 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? LANE_SMALL_CTAS : 4) 
       const bool act0 = f >= 0;
       // ---- pass 1: gather the node's samples of this lane's feature; min / max / hasMissing (pkg:34-54)
       const VT *col = CODED ? reinterpret_cast<const VT *>(p.C8) + (int64_t)(act0 ? f : 0) * p.ldc
-                            : reinterpret_cast<const VT *>(p.X) + (int64_t)(act0 ? f : 0) * p.ld;
+                            : nullptr;
+      const Col dcol = CODED ? Col{nullptr, nullptr, 0} : col_of(p, act0 ? f : 0);
       double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;  // pkg:35-36
       bool has_nan = false;
       // byte codes: K = 1 in a column that holds NaNs (stored byte 0 = NaN), else 0; t = byte - K is the
@@ -1665,7 +1666,7 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? LANE_SMALL_CTAS : 4) 
           mxb = max(mxb, b8);
           mnt = min(mnt, b8 - K);
         } else {
-          const double x = act0 ? __ldg(reinterpret_cast<const double *>(col) + rj) : 0.0;
+          const double x = act0 ? col_at(dcol, rj) : 0.0;
           s_x[pos * 32 + lane] = (VT)x;
           if (x < mn) mn = x;
           if (x > mx) mx = x;

@@ -445,11 +445,11 @@ __global__ void __launch_bounds__(WT) k_wide_pass1(P p, WState w) {
     __syncthreads();
     // groups of 4 candidates, four rows per thread and trip: 16 independent gathers in flight
     for (int g0 = 0; g0 < nb; g0 += 4) {
-      const double *colp[4];
+      Col colp[4];
 #pragma unroll
       for (int c = 0; c < 4; c++) {
         const int32_t f = (g0 + c < nb) ? cd.feat[g0 + c] : -1;
-        colp[c] = p.X + (int64_t)(f >= 0 ? f : 0) * p.ld;
+        colp[c] = col_of(p, f >= 0 ? f : 0);
       }
       double mn[4], mx[4];
       uint32_t nanm = 0u;
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(WT) k_wide_pass1(P p, WState w) {
 #pragma unroll
         for (int u2 = 0; u2 < 4; u2++)
 #pragma unroll
-          for (int c = 0; c < 4; c++) x[u2][c] = (r4[u2] >= 0) ? __ldg(colp[c] + r4[u2]) : NAN;
+          for (int c = 0; c < 4; c++) x[u2][c] = (r4[u2] >= 0) ? col_at(colp[c], r4[u2]) : NAN;
 #pragma unroll
         for (int u2 = 0; u2 < 4; u2++) {
 #pragma unroll
@@ -612,7 +612,7 @@ __device__ __forceinline__ void fp64_pass2(const P &p, const int32_t *s_feat, co
     uint32_t rowbits = 0u;
 #pragma unroll 8
     for (int c = 0; c < nb; c++) {
-      const double x = __ldg(p.X + (int64_t)s_feat[c] * p.ld + row);
+      const double x = col_at(col_of(p, s_feat[c]), row);
       const bool in = sweep ? (x != x) : (x < s_cut[c]);
       rowbits |= (uint32_t)in << c;
     }
@@ -733,11 +733,11 @@ __global__ void __launch_bounds__(WT) k_wide_pass2(P p, WState w) {
           }
           continue;
         }
-        const double *colp[4];
+        Col colp[4];
         double cut[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-          colp[c] = p.X + (int64_t)s_feat[min(g0 + c, 31)] * p.ld;
+          colp[c] = col_of(p, s_feat[min(g0 + c, 31)]);
           cut[c] = s_cut[min(g0 + c, 31)];
         }
         int32_t cnt[4];
@@ -760,7 +760,7 @@ __global__ void __launch_bounds__(WT) k_wide_pass2(P p, WState w) {
 #pragma unroll
           for (int u2 = 0; u2 < 4; u2++)
 #pragma unroll
-            for (int c = 0; c < 4; c++) x[u2][c] = (r4[u2] >= 0) ? __ldg(colp[c] + r4[u2]) : 0.0;
+            for (int c = 0; c < 4; c++) x[u2][c] = (r4[u2] >= 0) ? col_at(colp[c], r4[u2]) : 0.0;
 #pragma unroll
           for (int u2 = 0; u2 < 4; u2++) {
             const double yd2 = ET_MUL(yd[u2], yd[u2]);
@@ -1066,7 +1066,7 @@ __global__ void __launch_bounds__(WT) k_wide_count(P p, WState w) {
   const bool mil = nd.best_mil != 0;
   const double cut = nd.best_cut;
   const uint8_t *c8 = CODED ? p.C8 + (int64_t)bf * p.ldc : nullptr;
-  const double *col = p.X + (int64_t)bf * p.ld;
+  const Col col = CODED ? Col{nullptr, nullptr, 0} : col_of(p, bf);
   uint32_t *bits = w.bits + (int64_t)blockIdx.x * (w.chunk / 32);
   int32_t cntl = 0;
   for (int32_t j0 = wit * 32; j0 < r.cnt; j0 += WT) {
@@ -1079,7 +1079,7 @@ __global__ void __launch_bounds__(WT) k_wide_count(P p, WState w) {
         const bool isn = (K == 1) && (b8 == 0);
         left = isn ? mil : (((b8 - K) & 255) < thr);
       } else {
-        const double x = __ldg(col + row);
+        const double x = col_at(col, row);
         left = (x < cut) || (mil && (x != x));
       }
     }

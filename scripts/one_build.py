@@ -7,7 +7,7 @@ import lamp_b200 as et
 cfg = dict(bench.CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "mnist"])
 m = int(sys.argv[2]) if len(sys.argv) > 2 else cfg["trees"]
 builds = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-x, y = bench.make_data(cfg)
+x, y = bench.make_host_data(cfg)
 ctx = et.Context(0)
 dd = et.DeviceData.from_rowmajor(x, ctx)
 if cfg["task"] == "cls":

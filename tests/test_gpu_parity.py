@@ -335,7 +335,12 @@ def _sparse_table(n, d, density, seed):
     return np.array(colptr, np.int64), np.concatenate(rows), np.concatenate(vals)
 
 
-def test_csc_input_builds_the_forest_of_its_dense_expansion():
+@pytest.mark.parametrize("resident", ["sparse", "expanded"])
+def test_csc_input_builds_the_forest_of_its_dense_expansion(resident, monkeypatch):
+    """`sparse`: the table stays CSC in HBM (values found by binary search among a column's stored rows, zeros
+    implicit -- what a table too large for its dense form gets); `expanded`: small tables are expanded into the
+    resident dense matrix.  Either way the forest is the dense oracle's, bit for bit."""
+    monkeypatch.setenv("ETGPU_CSC_DENSE_MAX", "0" if resident == "sparse" else str(1 << 40))
     n, d = 20000, 500
     colptr, rowidx, vals = _sparse_table(n, d, 0.01, 4)
     dense = np.zeros((n, d))
@@ -350,8 +355,11 @@ def test_csc_input_builds_the_forest_of_its_dense_expansion():
     gf = et.buildForestClassification(dd, None, None, 2, 2, 100, 2, 2, seed=4, replay=oracle_replay(of))
     assert_trees_bit_exact(gf, of)
     assert np.array_equal(et.predictClassification(gf, dense[:3000]), of.predict(dense[:3000]))
-    # free-running: the CSC table and its dense expansion give the same forest
+    # free-running: the CSC table and its dense expansion give the same forest (a sparse-resident table is read as
+    # FP64, so its dense twin must not be byte-coded: small coded nodes draw from their varying features only)
     f1 = et.buildForestClassification(dd, None, None, 2, 2, 100, 3, 2, seed=9)
+    if resident == "sparse":
+        monkeypatch.setenv("ETGPU_NO_CODES", "1")
     f2 = et.buildForestClassification(dense, y, None, 2, 2, 100, 3, 2, seed=9)
     a, b = f1.export_packed(), f2.export_packed()
     for field in ("feat", "right_or_leaf"):
@@ -374,6 +382,40 @@ def test_scipy_sparse_matrix_is_accepted():
     assert np.array_equal(a["cut"].view(np.int64), b["cut"].view(np.int64)) and np.array_equal(a["leaf"], b["leaf"])
 
 
+def test_csc_unsorted_rows_duplicates_and_regression(monkeypatch):
+    """Unsorted columns are sorted on the host and a row listed twice keeps the LATER entry (deterministically), in
+    both resident forms; regression and weighted classification read a sparse-resident table through the same
+    loader."""
+    rng = np.random.default_rng(3)
+    n, d = 4000, 30
+    dense = np.where(rng.random((n, d)) < 0.08, np.round(rng.normal(size=(n, d)), 2), 0.0)
+    dense[rng.random((n, d)) < 0.01] = np.nan  # stored NaNs are missing values like anywhere else
+    colptr, rows, vals = [0], [], []
+    for c in range(d):
+        r = np.flatnonzero((dense[:, c] != 0) | np.isnan(dense[:, c])).astype(np.int32)
+        v = dense[r, c]
+        dup = r[: min(5, len(r))]  # the first rows again, EARLIER in the list, with junk values: the later entry wins
+        r2, v2 = np.concatenate([dup, r]), np.concatenate([np.full(len(dup), 99.0), v])
+        perm = np.concatenate([np.arange(len(dup)), len(dup) + rng.permutation(len(r))])  # unsorted, duplicates first
+        rows.append(r2[perm])
+        vals.append(v2[perm])
+        colptr.append(colptr[-1] + len(r2))
+    colptr, rows, vals = np.array(colptr, np.int64), np.concatenate(rows), np.concatenate(vals)
+    yr = np.nan_to_num(dense[:, :5]).sum(axis=1) + 0.1 * rng.normal(size=n)
+    yc = (yr > np.median(yr)).astype(np.int32)
+    w = rng.gamma(2.0, size=n)
+    ofr = O.build_forest_regression(dense, yr, 3, 5, 3, 2, seed=6, record_trace=True)
+    ofw = O.build_forest_classification(dense, yc, w, 2, 2, 5, 3, 2, seed=7, record_trace=True)
+    for dense_max in ("0", str(1 << 40)):
+        monkeypatch.setenv("ETGPU_CSC_DENSE_MAX", dense_max)
+        dd = et.DeviceData.from_csc(colptr, rows, vals, n, d)
+        gfr = et.buildForestRegression(dd, yr, 3, 5, 3, 2, seed=6, replay=oracle_replay(ofr))
+        assert_trees_bit_exact(gfr, ofr)
+        gfw = et.buildForestClassification(dd, yc, w, 2, 2, 5, 3, 2, seed=7, replay=oracle_replay(ofw))
+        assert_trees_bit_exact(gfw, ofw)
+        dd.free()
+
+
 def test_csc_input_argument_errors():
     with pytest.raises(ValueError):  # row index outside the table
         et.DeviceData.from_csc([0, 1], [7], [1.0], 5, 1)
@@ -392,7 +434,7 @@ def test_full_size_mnist_shaped_properties(table_coding):
     vote is the mean of the per-tree votes."""
     import bench
     cfg = bench.CONFIGS["mnist"]
-    x, y = bench.make_data(cfg)
+    x, y = bench.make_host_data(cfg)
     m = 8
     f = et.buildForestClassification(x, y, None, cfg["C"], cfg["n_min"], cfg["k"], m, 8, seed=77)
     ser = f.export_packed()
@@ -505,3 +547,45 @@ def test_resident_target_with_per_call_weights(mnist):
         for other in (got, again):
             assert np.array_equal(ref.flat(t).feature, other.flat(t).feature)
             assert np.array_equal(ref.flat(t).leaf, other.flat(t).leaf)
+
+
+# ---- replay at BASELINE sizes (one tree each; the oracle runs once per module) -----------------------------------
+@pytest.fixture(scope="module")
+def mnist_shaped_60k():
+    """BASELINE configs[1]'s table from bench.py's generator (60000 x 784, 10 classes) and one oracle tree."""
+    import bench
+    x, y = bench.gen_mnist_like(60000, 784, 10, 20260201)
+    of = O.build_forest_classification(x, y, None, 10, 2, 28, 1, 1, seed=3, record_trace=True)
+    return x, y, of
+
+
+def test_replay_at_size_mnist_shaped_60000x784(mnist_shaped_60k):
+    x, y, of = mnist_shaped_60k
+    gf = et.buildForestClassification(x, y, None, 10, 2, 28, 1, 1, seed=3, replay=oracle_replay(of))
+    assert_trees_bit_exact(gf, of)
+    so, sg = of.stats(), gf.stats
+    for key in ("v_mm", "v_sc", "s_rows", "p_rows", "draws", "const_hits", "scored", "nodes"):
+        assert so[key] == sg[key], (key, so[key], sg[key])
+    assert np.array_equal(et.predictClassification(gf, x[:5000]), of.predict(x[:5000]))
+
+
+@pytest.fixture(scope="module")
+def regression_1m():
+    """BASELINE configs[2]'s table from bench.py's generator (1M x 100, nMin = 5, k = 10) and one oracle tree."""
+    import bench
+    x, y = bench.gen_regression(1_000_000, 100, 3)
+    of = O.build_forest_regression(x, y, 5, 10, 1, 1, seed=4, record_trace=True)
+    return x, y, of
+
+
+def test_replay_at_size_regression_1Mx100(regression_1m, table_coding):
+    if table_coding.startswith("codes"):
+        pytest.skip("continuous table: never byte-coded (same run as the fp64 variant)")
+    x, y, of = regression_1m
+    gf = et.buildForestRegression(x, y, 5, 10, 1, 1, seed=4, replay=oracle_replay(of))
+    # nodes of more than 2048 rows are scored from fixed-shape parallel sums: the structure is the reference's as
+    # long as no such split was decided by less than 1e-9 (relative); the count is part of the result
+    assert gf.stats["parallel_sum_nodes"] > 0
+    assert gf.stats["ambiguous_splits"] == 0
+    assert_trees_bit_exact(gf, of)
+    assert np.array_equal(et.predictRegression(gf, x[:20000]), of.predict(x[:20000]))

@@ -134,3 +134,21 @@ def test_wire_format_forest_roundtrip_is_bit_exact():
     trees = [flat_to_adt(FlatTree(t.feature, t.cut, t.mil, t.left, t.right, t.leaf), True) for t in of.trees()]
     back = wire.forest_from_json(wire.forest_to_json(trees))
     assert back == trees  # dataclass equality: every cutpoint and leaf mean identical as floats
+
+
+def test_jni_shim_compiles_against_the_header_and_matches_the_scala_natives():
+    """jni/etgpu_jni.c is syntax-checked with gcc against include/etgpu.h and a declaration-only jni.h (this image
+    has no JDK); its exported names are exactly the @native methods of scala/lamp/extratrees/gpu/EtGpu.scala."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "jni", "etgpu_jni.c")
+    subprocess.check_call(["gcc", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "jni", "stub"),
+                           "-I" + os.path.join(root, "include"), src])
+    exported = set(re.findall(r"Java_lamp_extratrees_gpu_Native_(\w+)\(", open(src).read()))
+    scala = open(os.path.join(root, "scala", "lamp", "extratrees", "gpu", "EtGpu.scala")).read()
+    natives = set(re.findall(r"@native def (\w+)\(", scala))
+    assert exported == natives and len(natives) >= 9, (exported ^ natives)
+    header = open(os.path.join(root, "include", "etgpu.h")).read()
+    for fn in set(re.findall(r"\b(et_\w+)\(", open(src).read())):
+        assert re.search(r"\b%s\(" % fn, header), fn
