@@ -119,6 +119,7 @@ struct EventPair {
 // ---- gathered forest: staging (rank-major) -> tree order --------------------------------------------------------
 struct TreeMove {
   int64_t src_node, dst_node, src_leaf, dst_leaf;  // offsets in the staging buffers / the gathered forest
+  int64_t leaf_local;                              // first leaf of the tree in its shard's own leaf numbering
   int32_t n_nodes, pad_;
 };
 
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256) k_forest_permute(const TreeMove *__restri
                                                         const double *__restrict__ sleaves, int lw, PNode *__restrict__ nodes,
                                                         double *__restrict__ leaves) {
   const TreeMove m = mv[blockIdx.x];
-  const int64_t dl = m.dst_leaf - m.src_leaf;
+  const int64_t dl = m.dst_leaf - m.leaf_local;  // (a leaf node holds its index in the SHARD's leaf table)
   for (int32_t j = threadIdx.x; j < m.n_nodes; j += 256) {
     PNode pn = snodes[m.src_node + j];
     if (pn.feat < 0) pn.right_or_leaf = (int32_t)(pn.right_or_leaf + dl);
@@ -197,7 +198,7 @@ et_forest *forest_allgather_rank(et_ctx *ctx, et_forest *shard) {
   CUDA_CHECK(cudaStreamSynchronize(st));
   // ---- plan: trees in order of their key
   struct Src {
-    int64_t key, node, leaf;
+    int64_t key, node, leaf, leaf_local;
     int32_t n_nodes;
   };
   std::vector<Src> src;
@@ -206,7 +207,7 @@ et_forest *forest_allgather_rank(et_ctx *ctx, et_forest *shard) {
     int64_t no = node0[(size_t)r], lo = leaf0[(size_t)r];
     for (int64_t t = 0; t < all[(size_t)4 * r]; t++) {
       const int64_t key = all_meta[meta.size() * r + (size_t)2 * t], nn = all_meta[meta.size() * r + (size_t)2 * t + 1];
-      src.push_back(Src{key, no, lo, (int32_t)nn});
+      src.push_back(Src{key, no, lo, lo - leaf0[(size_t)r], (int32_t)nn});
       no += nn;
       lo += (nn + 1) / 2;
     }
@@ -225,7 +226,7 @@ et_forest *forest_allgather_rank(et_ctx *ctx, et_forest *shard) {
   std::vector<TreeMove> mv((size_t)m_tot);
   int64_t dn = 0, dl = 0;
   for (size_t t = 0; t < src.size(); t++) {
-    mv[t] = TreeMove{src[t].node, dn, src[t].leaf, dl, src[t].n_nodes, 0};
+    mv[t] = TreeMove{src[t].node, dn, src[t].leaf, dl, src[t].leaf_local, src[t].n_nodes, 0};
     f->tree_off[t] = dn;
     f->order_key[t] = src[t].key;
     dn += src[t].n_nodes;
