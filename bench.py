@@ -301,7 +301,7 @@ class Bench:
         self.m = cfg["trees"]
         from lamp_b200 import dist as D
         self.ids = D.shard_tree_ids(self.m, rank, world)  # strong scaling: the forest is fixed, its trees are sharded
-        self.x_host = self.y = self.csc = self.x_dev = self.x_pred_dev = None
+        self.x_host = self.y = self.csc = self.x_dev = self.x_pred_dev = self.x_pageable = None
         self.pinned = {}
         self._make_data()
 
@@ -378,7 +378,7 @@ class Bench:
         ser = f.export_packed(self.pinned["nodes"], self.pinned["leaves"])
         return ser["nodes"].nbytes + ser["leaves"].nbytes + ser["tree_off"].nbytes
 
-    def build_e2e(self, seed):
+    def build_e2e(self, seed, pageable=False):
         """The public API with HOST buffers: H2D of the table (pinned), transpose + coding, build, [gather], and the
         device -> host read of the step's result, the serialized forest (packed device layout).  N > 1: rank 0
         uploads, the replicas travel over NVLink (et_data_broadcast), every rank builds its shard, the trees are
@@ -390,7 +390,9 @@ class Bench:
                 f = self.build(dd, self.y, seed)
                 dd.free()
             else:
-                f = self.build(self.x_host, self.y, seed)
+                if pageable and self.x_pageable is None:
+                    self.x_pageable = np.array(self.x_host)  # an ordinary (pageable) host array, like a JVM heap array
+                f = self.build(self.x_pageable if pageable else self.x_host, self.y, seed)
             return self.export_pinned(f)
         dd0 = et.DeviceData.from_rowmajor(self.x_host, self.ctx) if self.rank == 0 else None
         dd = self.D.broadcast_data(self.ctx, dd0, 0)
@@ -475,7 +477,16 @@ def measure(b, steps, warmup, want_e2e=True, want_cpu=True, clocks_device=None, 
         el = reduce(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
         d2h = reduce(float(d2h), dist.ReduceOp.SUM if world > 1 else None)
         e2e = {"value": b.m * steps / el, "unit": "trees/s", "h2d_bytes_per_step": b.h2d_bytes(),
-               "d2h_bytes_per_step": int(d2h) // max(steps, 1)}
+               "d2h_bytes_per_step": int(d2h) // max(steps, 1), "host_input": "pinned"}
+        if world == 1 and b.x_host is not None and cfg.get("_main"):
+            # the same from an ordinary pageable array (what a JVM / numpy caller holds): the library stages it
+            # through its own pinned bounce buffers (api.cu et_h2d)
+            b.build_e2e(5000, pageable=True)
+            t0 = time.perf_counter()
+            for s in range(steps):
+                b.build_e2e(6000 + s, pageable=True)
+            torch.cuda.synchronize()
+            e2e["pageable_input_value"] = b.m * steps / (time.perf_counter() - t0)
 
     # ---- predict ---------------------------------------------------------------------------------------------
     n_pred, d_pred = b.x_pred_dev.shape

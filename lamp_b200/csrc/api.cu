@@ -2,7 +2,9 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <memory>
+#include <thread>
 
 #include "internal.h"
 
@@ -84,6 +86,122 @@ void et_dev_free(et_ctx *ctx, void *p, size_t bytes) {
   ctx->cache_bytes += bytes;
 }
 
+// ---- uploads from pageable host memory -------------------------------------------------------------------
+// (the ingest path of the reference, lamp-saddle SaddleTensorHelpers.scala:156-176: Mat.toArray -> native copy ->
+// device; a JVM caller hands over a pageable heap array)
+struct HostStager {
+  static constexpr size_t PIECE = (size_t)8 << 20;
+  void *buf[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool used[2] = {false, false};
+  // copy threads: a job is one memcpy cut into slices
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv_job, cv_done;
+  const char *src = nullptr;
+  char *dst = nullptr;
+  size_t len = 0;
+  int gen = 0, pending = 0;
+  bool stop = false;
+  void run(int t, int T) {
+    int seen = 0;
+    for (;;) {
+      const char *s;
+      char *d;
+      size_t n;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_job.wait(lk, [&] { return stop || gen != seen; });
+        if (stop) return;
+        seen = gen;
+        s = src;
+        d = dst;
+        n = len;
+      }
+      const size_t a = n * (size_t)t / (size_t)T, b = n * (size_t)(t + 1) / (size_t)T;
+      if (b > a) memcpy(d + a, s + a, b - a);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (--pending == 0) cv_done.notify_one();
+      }
+    }
+  }
+  void copy(char *d, const char *s, size_t n) {  // parallel memcpy, returns when done
+    const int T = (int)workers.size();
+    if (T == 0) {
+      memcpy(d, s, n);
+      return;
+    }
+    std::unique_lock<std::mutex> lk(mu);
+    src = s;
+    dst = d;
+    len = n;
+    pending = T;
+    gen++;
+    cv_job.notify_all();
+    cv_done.wait(lk, [&] { return pending == 0; });
+  }
+};
+
+void et_stager_free(HostStager *s) {
+  if (!s) return;
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->stop = true;
+  }
+  s->cv_job.notify_all();
+  for (auto &t : s->workers) t.join();
+  for (int i = 0; i < 2; i++) {
+    if (s->buf[i]) cudaFreeHost(s->buf[i]);
+    if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+  }
+  delete s;
+}
+
+void et_h2d(et_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return;
+  cudaPointerAttributes at;
+  bool pageable = true;
+  if (cudaPointerGetAttributes(&at, src_host) == cudaSuccess)
+    pageable = (at.type == cudaMemoryTypeUnregistered);
+  else
+    cudaGetLastError();
+  static const bool off = getenv("ETGPU_NO_STAGER") != nullptr && atoi(getenv("ETGPU_NO_STAGER")) != 0;
+  if (!pageable || off || bytes < ((size_t)1 << 20)) {
+    CUDA_CHECK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));
+    return;
+  }
+  if (!ctx->stager) {
+    std::unique_ptr<HostStager> s(new HostStager());
+    for (int i = 0; i < 2; i++) {
+      if (cudaHostAlloc(&s->buf[i], HostStager::PIECE, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        for (int j = 0; j < i; j++) cudaFreeHost(s->buf[j]);
+        s->buf[0] = s->buf[1] = nullptr;
+        CUDA_CHECK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));  // no pinned memory: plain path
+        return;
+      }
+      CUDA_CHECK(cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming));
+    }
+    const int T = (int)std::max(1u, std::min(4u, std::thread::hardware_concurrency() / 2));
+    HostStager *raw = s.get();
+    for (int t = 0; t < T; t++) raw->workers.emplace_back([raw, t, T] { raw->run(t, T); });
+    ctx->stager = s.release();
+  }
+  HostStager &S = *ctx->stager;
+  const char *src = static_cast<const char *>(src_host);
+  char *dst = static_cast<char *>(dst_dev);
+  int b = 0;
+  for (size_t off2 = 0; off2 < bytes; off2 += HostStager::PIECE, b ^= 1) {
+    const size_t n = std::min(HostStager::PIECE, bytes - off2);
+    if (S.used[b]) CUDA_CHECK(cudaEventSynchronize(S.ev[b]));  // the DMA that last read this buffer is done
+    S.copy(static_cast<char *>(S.buf[b]), src + off2, n);      // (the other buffer's DMA runs meanwhile)
+    CUDA_CHECK(cudaMemcpyAsync(dst + off2, S.buf[b], n, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaEventRecord(S.ev[b], st));
+    S.used[b] = true;
+  }
+}
+
 // ---- context --------------------------------------------------------------------------------
 extern "C" int et_init(int32_t device, et_ctx **out) {
   ET_API_BEGIN
@@ -162,6 +280,7 @@ static void ctx_destroy(et_ctx *ctx) {
     if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  et_stager_free(ctx->stager);
   if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
   if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
   et_workspace_free(ctx->ws);
@@ -337,30 +456,58 @@ extern "C" int et_data_dense_rowmajor(et_ctx *ctx, const double *x, int64_t n, i
   CUDA_CHECK(cudaSetDevice(ctx->device));
   et_data *D = data_alloc(ctx, n, d);
   if (n > 0 && d > 0) {
-    // staged in row chunks of <= 256 MB so the temporary stays small next to the table
-    int64_t chunk = std::max<int64_t>(1, ((int64_t)256 << 20) / ((int64_t)d * 8));
+    // Staged in row chunks through TWO device buffers: the host->device copy of chunk c + 1 (copy stream) overlaps
+    // the transpose of chunk c (compute stream).  Pageable sources go through the pinned stager (et_h2d).
+    int64_t chunk = std::max<int64_t>(1, ((int64_t)64 << 20) / ((int64_t)d * 8));
     chunk = std::min(chunk, n);
     const size_t stage_bytes = (size_t)chunk * d * sizeof(double);
-    double *stage = static_cast<double *>(et_dev_alloc(ctx, stage_bytes));
-    if (!stage) {
+    double *stage[2] = {static_cast<double *>(et_dev_alloc(ctx, stage_bytes)), nullptr};
+    stage[1] = (chunk < n) ? static_cast<double *>(et_dev_alloc(ctx, stage_bytes)) : stage[0];
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    auto cleanup = [&]() {
+      et_dev_free(ctx, stage[0], stage_bytes);
+      if (stage[1] != stage[0]) et_dev_free(ctx, stage[1], stage_bytes);
+      for (int i = 0; i < 2; i++) {
+        if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
+        if (ev_free[i]) cudaEventDestroy(ev_free[i]);
+      }
+    };
+    if (!stage[0] || !stage[1]) {
+      cleanup();
       et_data_free(D);
-      ET_FAIL(ET_ENOMEM, "cannot allocate the upload staging buffer");
+      ET_FAIL(ET_ENOMEM, "cannot allocate the upload staging buffers");
     }
     try {
-      for (int64_t r0 = 0; r0 < n; r0 += chunk) {
-        int64_t rows = std::min(chunk, n - r0);
-        CUDA_CHECK(cudaMemcpyAsync(stage, x + r0 * d, (size_t)rows * d * sizeof(double), cudaMemcpyHostToDevice,
-                                   ctx->stream));
-        et_launch_transpose(ctx, stage, rows, d, D->x, D->ld, r0);
+      cudaStream_t copy_st = ctx->side[0];
+      for (int i = 0; i < 2; i++) {
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
+      }
+      CUDA_CHECK(cudaEventRecord(ev_free[0], ctx->stream));  // (earlier work on the compute stream comes first)
+      CUDA_CHECK(cudaStreamWaitEvent(copy_st, ev_free[0], 0));
+      int b = 0;
+      bool used[2] = {false, false};
+      for (int64_t r0 = 0; r0 < n; r0 += chunk, b ^= 1) {
+        const int64_t rows = std::min(chunk, n - r0);
+        if (used[b]) CUDA_CHECK(cudaStreamWaitEvent(copy_st, ev_free[b], 0));  // its last transpose has read it
+        et_h2d(ctx, stage[b], x + r0 * d, (size_t)rows * d * sizeof(double), copy_st);
+        CUDA_CHECK(cudaEventRecord(ev_copied[b], copy_st));
+        CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ev_copied[b], 0));
+        et_launch_transpose(ctx, stage[b], rows, d, D->x, D->ld, r0);
+        CUDA_CHECK(cudaEventRecord(ev_free[b], ctx->stream));
+        used[b] = true;
       }
       et_data_encode(ctx, D);
       CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(copy_st));
     } catch (...) {
-      et_dev_free(ctx, stage, stage_bytes);
+      cudaStreamSynchronize(ctx->stream);
+      cudaStreamSynchronize(ctx->side[0]);
+      cleanup();
       et_data_free(D);
       throw;
     }
-    et_dev_free(ctx, stage, stage_bytes);
+    cleanup();
   }
   *out = D;
   ET_API_END
@@ -1147,9 +1294,7 @@ void et_predict_host_impl(et_ctx *ctx, et_forest *f, const double *x, int64_t n,
   try {
     for (int64_t r0 = 0; r0 < n; r0 += chunk) {
       int64_t rows = std::min(chunk, n - r0);
-      if (d > 0)
-        CUDA_CHECK(cudaMemcpyAsync(dx, x + r0 * d, (size_t)rows * d * sizeof(double), cudaMemcpyHostToDevice,
-                                   ctx->stream));
+      if (d > 0) et_h2d(ctx, dx, x + r0 * d, (size_t)rows * d * sizeof(double), ctx->stream);
       et_predict_device_impl(ctx, f, dx, rows, d, dout, sum_only);
       CUDA_CHECK(cudaMemcpyAsync(out + r0 * lw, dout, (size_t)rows * lw * sizeof(double), cudaMemcpyDeviceToHost,
                                  ctx->stream));

@@ -168,8 +168,10 @@ struct Workspace {
   DevBuf<Counters> cnt;
   DevBuf<int64_t> tree_off, leaf_off;
   WideBufs *wide = nullptr;
+  Counters *h_cnt = nullptr;  // pinned: the per-level readback of the counters is a plain DMA
   ~Workspace() {
     if (wide) wide_bufs_destroy(wide);
+    if (h_cnt) cudaFreeHost(h_cnt);
   }
 };
 
@@ -190,6 +192,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
   if (!ctx->ws) ctx->ws = new Workspace();
   Workspace &ws = *ctx->ws;
   if (!ws.wide) ws.wide = wide_bufs_create();
+  if (!ws.h_cnt) CUDA_CHECK(cudaHostAlloc((void **)&ws.h_cnt, sizeof(Counters), cudaHostAllocDefault));
   et_stats S;
   memset(&S, 0, sizeof(S));
   const int64_t launches0 = ctx->launches;
@@ -335,7 +338,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       const size_t ns = (size_t)Bt * (size_t)n;
       pt.start();
       for (int q = 0; q < 2; q++) {
-        ws.idx[q].ensure(ns, 1.0);
+        ws.idx[q].ensure(ns + 8, 1.0);  // (+ slack: bulk copies of a segment are rounded up to 16 bytes)
         if (task == TASK_REG)
           ws.yr[q].ensure(ns, 1.0);
         else
@@ -415,7 +418,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       int64_t wide_rows = (size_class(p, n) == Q_WIDE) ? (int64_t)Bt * n : 0;
       int64_t big_rows = (n > NM_MAX) ? (int64_t)Bt * n : 0;
       int64_t leaf_bound = 0;  // upper bound of the leaves allocated so far
-      Counters hc;
+      Counters &hc = *ws.h_cnt;
       memset(&hc, 0, sizeof(hc));
       while (F > 0) {
         NvtxRange nv_level("etgpu.level");

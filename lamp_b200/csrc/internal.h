@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 struct Workspace;  // build.cu: device buffers reused across builds
+struct HostStager;  // api.cu: pinned bounce buffers + copy threads for uploads from pageable host memory
 
 struct et_ctx {
   int device = 0;
@@ -33,6 +34,7 @@ struct et_ctx {
   double comm_ms = 0.0;
   std::vector<et_ctx *> peers;
   bool is_multi() const { return !peers.empty(); }
+  HostStager *stager = nullptr;
   // et_data / et_forest handles still alive on this context: et_shutdown with handles outstanding is deferred until
   // the last of them is freed (a handle's destructor needs the context's mutex and block cache)
   int live_handles = 0;
@@ -157,6 +159,11 @@ void et_build_forest(et_ctx *ctx, et_data *data, const BuildArgs &a, et_forest *
 void et_predict_device_impl(et_ctx *ctx, et_forest *f, const double *x_dev, int64_t n, int32_t d,
                             double *out_dev, int sum_only);
 // api.cu
+// host -> device copy on `st`: pinned sources go straight to the copy engine; pageable ones (a JVM heap array, a
+// numpy array) are staged through two pinned bounce buffers filled by a few copy threads while the previous piece
+// is in flight, instead of the driver's single-threaded pageable path.  Returns after the source has been read.
+void et_h2d(et_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t st);
+void et_stager_free(HostStager *s);
 et_data *et_data_alloc_internal(et_ctx *ctx, int64_t n, int32_t d);
 void et_predict_host_impl(et_ctx *ctx, et_forest *f, const double *x, int64_t n, int32_t d, double *out, int sum_only,
                           int want_regression);

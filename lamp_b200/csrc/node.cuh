@@ -1488,53 +1488,57 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? LANE_SMALL_CTAS : 4) 
     bool use_nc = false;
     if (SMALL && CODED && !p.replay && p.R8 != nullptr && p.r8_stride <= 1024 && n <= p.nc_max) {
       use_nc = true;
-      const int nword = p.r8_stride >> 2;
-      const uint32_t *cof4 = reinterpret_cast<const uint32_t *>(p.coff);
-      for (int h2 = 0; h2 < 2; h2++) {  // table words lane + 32 i, i = 4 h2 .. 4 h2 + 3
-        if (h2 * 128 >= nword) {
-          for (int w0 = h2 * 16 + lane; w0 < W; w0 += 32) s_taken[w0] = 0xffffffffu;
-          continue;
-        }
-        uint32_t first[4], acc[4];
-        {
-          const uint32_t *rp = reinterpret_cast<const uint32_t *>(p.R8 + (int64_t)idx[0] * p.r8_stride);
+      // 16-byte loads: lane q of a trip owns features 16 q .. 16 q + 15 of the row (two trips cover 1024 features)
+      const int nchunk = p.r8_stride >> 4;
+      const uint4 *cof16 = reinterpret_cast<const uint4 *>(p.coff);
+      uint4 first[2], acc[2];
+      {
+        const uint4 *rp = reinterpret_cast<const uint4 *>(p.R8 + (int64_t)idx[0] * p.r8_stride);
 #pragma unroll
-          for (int i4 = 0; i4 < 4; i4++) {
-            const int tw = (h2 * 4 + i4) * 32 + lane;
-            first[i4] = (tw < nword) ? __ldg(rp + tw) : 0u;
-            acc[i4] = 0u;
-          }
+        for (int it = 0; it < 2; it++) {
+          const int q16 = it * 32 + lane;
+          first[it] = (q16 < nchunk) ? __ldg(rp + q16) : make_uint4(0u, 0u, 0u, 0u);
+          acc[it] = make_uint4(0u, 0u, 0u, 0u);
         }
-        for (int w = 0; w < nw; w++) {
-          const int j0 = w << 5, cnt = min(32, n - j0);
-          const int32_t row = (lane < cnt) ? idx[j0 + lane] : 0;
-          for (int jj = (w == 0) ? 1 : 0; jj < cnt; jj++) {
-            const uint32_t *rp =
-                reinterpret_cast<const uint32_t *>(p.R8 + (int64_t)__shfl_sync(FULL, row, jj) * p.r8_stride);
+      }
+      for (int w = 0; w < nw; w++) {
+        const int j0 = w << 5, cnt = min(32, n - j0);
+        const int32_t row = (lane < cnt) ? idx[j0 + lane] : 0;
+        for (int jj = (w == 0) ? 1 : 0; jj < cnt; jj++) {
+          const uint4 *rp = reinterpret_cast<const uint4 *>(p.R8 + (int64_t)__shfl_sync(FULL, row, jj) * p.r8_stride);
 #pragma unroll
-            for (int i4 = 0; i4 < 4; i4++) {
-              const int tw = (h2 * 4 + i4) * 32 + lane;
-              if (tw < nword) acc[i4] |= __ldg(rp + tw) ^ first[i4];
+          for (int it = 0; it < 2; it++) {
+            const int q16 = it * 32 + lane;
+            if (q16 < nchunk) {
+              const uint4 v = __ldg(rp + q16);
+              acc[it].x |= v.x ^ first[it].x;
+              acc[it].y |= v.y ^ first[it].y;
+              acc[it].z |= v.z ^ first[it].z;
+              acc[it].w |= v.w ^ first[it].w;
             }
           }
         }
+      }
 #pragma unroll
-        for (int i4 = 0; i4 < 4; i4++) {
-          const int tw = (h2 * 4 + i4) * 32 + lane;
-          uint32_t bits = 0u;
-          if (tw < nword) {
-            const uint32_t k4 = __ldg(cof4 + tw);                                  // 0 = the column holds NaNs
-            const uint32_t nan4 = __vcmpeq4(first[i4], 0u) & __vcmpeq4(k4, 0u);    // the first row is NaN there
-            const uint32_t ne4 = __vcmpne4(acc[i4], 0u) | nan4;                    // 0xff per varying feature
-            bits = ((ne4 & 0x01010101u) * 0x01020408u) >> 24;                      // 4 bits, feature order
-          }
-          uint32_t word = bits << (4 * (lane & 7));
-          word |= __shfl_xor_sync(FULL, word, 1);
-          word |= __shfl_xor_sync(FULL, word, 2);
-          word |= __shfl_xor_sync(FULL, word, 4);
-          const int w0 = (h2 * 4 + i4) * 4 + (lane >> 3);
-          if ((lane & 7) == 0 && w0 < W) s_taken[w0] = ~word;  // taken = not varying (padding included)
+      for (int it = 0; it < 2; it++) {
+        const int q16 = it * 32 + lane;
+        uint32_t bits = 0u;  // 16 bits, feature order: bit b = feature 16 q + b varies over the node's rows
+        if (q16 < nchunk) {
+          const uint4 k4 = __ldg(cof16 + q16);  // byte 0 = the column holds NaNs
+          auto vary4 = [](uint32_t a, uint32_t f, uint32_t k) -> uint32_t {
+            const uint32_t nan4 = __vcmpeq4(f, 0u) & __vcmpeq4(k, 0u);  // the first row is NaN there
+            const uint32_t ne4 = __vcmpne4(a, 0u) | nan4;               // 0xff per varying feature
+            return ((ne4 & 0x01010101u) * 0x01020408u) >> 24;           // 4 bits, feature order
+          };
+          bits = vary4(acc[it].x, first[it].x, k4.x) | (vary4(acc[it].y, first[it].y, k4.y) << 4) |
+                 (vary4(acc[it].z, first[it].z, k4.z) << 8) | (vary4(acc[it].w, first[it].w, k4.w) << 12);
         }
+        uint32_t word = bits << (16 * (lane & 1));
+        word |= __shfl_xor_sync(FULL, word, 1);
+        const int w0 = q16 >> 1;
+        // taken = not varying (padding included), or excluded on the path from the root: a feature that scored NaN
+        // at an ancestor stays out of the whole subtree (pkg:283-285) even if it varies here
+        if ((lane & 1) == 0 && w0 < W) s_taken[w0] = ~word | s_const[w0];
       }
       __syncwarp();
       int nc = 0;

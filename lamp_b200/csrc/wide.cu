@@ -27,6 +27,7 @@
 // reference's Gini expression).  Regression nodes of this size are scored from fixed-shape parallel moment sums
 // like the one-CTA path before (et_stats.parallel_sum_nodes / ambiguous_splits); weighted classification keeps the
 // one-CTA path (sequential weight sums).
+#include "bulk.cuh"
 #include "node.cuh"
 
 namespace etb {
@@ -74,7 +75,27 @@ struct WState {
   unsigned long long *pending;  // [0] nodes that drew a batch this round
   int32_t chunk;                // rows per chunk
   int32_t count;
+  int32_t bulk;                 // stage a chunk's sample-index segment with one TMA bulk copy (else plain loads)
 };
+
+// Stages `cnt` sample indices of a node's contiguous segment in shared memory (s_buf: 16-byte aligned, room for
+// cnt + 8 entries) and returns where entry 0 landed.  bulk: ONE thread queues a cp.async.bulk of the whole segment
+// (start rounded down / size rounded up to 16 bytes: the index buffers carry that much slack) and every thread
+// waits on the mbarrier after doing its other set-up work; else every thread copies its share.
+__device__ __forceinline__ const int32_t *stage_rows(int32_t *s_buf, const int32_t *src, int32_t cnt, uint64_t *bar,
+                                                     int bulk, int tid) {
+  if (bulk) {
+    const int lead = (int)(((uintptr_t)src & 15u) >> 2);
+    const uint32_t bytes = (uint32_t)(((lead + cnt) * 4 + 15) & ~15);
+    if (tid == 0) {
+      mbar_arrive_expect_tx(bar, bytes);
+      bulk_copy_g2s(s_buf, src - lead, bytes, bar);
+    }
+    return s_buf + lead;
+  }
+  for (int32_t j = tid; j < cnt; j += WT) s_buf[j] = src[j];
+  return s_buf;
+}
 
 // order-preserving 64-bit key of a non-NaN double (-0.0 and +0.0 share a key: the reference's `<` / `>` cannot
 // tell them apart and the cutpoint min + (max - min) * u does not depend on the sign of a zero bound)
@@ -403,7 +424,7 @@ __global__ void __launch_bounds__(WT) k_wide_pass1(P p, WState w) {
   __shared__ __align__(4) uint8_t s_Kb[32];
   __shared__ double s_mm[(WT / 32) * 8];
   __shared__ uint32_t s_nan[WT / 32];
-  int32_t *s_rows = reinterpret_cast<int32_t *>(smem_raw);
+  __shared__ __align__(8) uint64_t s_bar;
   ChunkRef r;
   if (!chunk_ref(w, blockIdx.x, r)) return;
   const WNode &nd = w.node[r.q];
@@ -411,14 +432,19 @@ __global__ void __launch_bounds__(WT) k_wide_pass1(P p, WState w) {
   if ((nd.flags & 2) || nb <= 0) return;
   WCand &cd = w.cand[r.q];
   const int tid = threadIdx.x, lane = tid & 31, wit = tid >> 5;
-  const int32_t *rr = p.idx_src + (int64_t)nd.tree * p.n + nd.b + r.j0;
-  for (int32_t j = tid; j < r.cnt; j += WT) s_rows[j] = rr[j];
+  if (w.bulk) {
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+  }
+  const int32_t *s_rows = stage_rows(reinterpret_cast<int32_t *>(smem_raw), p.idx_src + (int64_t)nd.tree * p.n + nd.b + r.j0,
+                                     r.cnt, &s_bar, w.bulk, tid);
   if (CODED) {
     if (tid < 32) {
       const int32_t f = (tid < nb) ? cd.feat[tid] : -1;
       s_coloff[tid] = (int64_t)(f >= 0 ? f : 0) * p.ldc;
       s_Kb[tid] = (f >= 0 && p.coff[f] == 0) ? 1 : 0;  // wide code - 1 = byte - K (mod 256)
     }
+    if (w.bulk) mbar_wait(&s_bar, 0);
     __syncthreads();
     const int ng = (nb + 3) >> 2;
     const uint32_t *s_K4 = reinterpret_cast<const uint32_t *>(s_Kb);
@@ -442,6 +468,7 @@ __global__ void __launch_bounds__(WT) k_wide_pass1(P p, WState w) {
       atomicMin(&cd.mnB[c], mnb);
     }
   } else {
+    if (w.bulk) mbar_wait(&s_bar, 0);
     __syncthreads();
     // groups of 4 candidates, four rows per thread and trip: 16 independent gathers in flight
     for (int g0 = 0; g0 < nb; g0 += 4) {
@@ -652,14 +679,17 @@ __global__ void __launch_bounds__(WT) k_wide_pass2(P p, WState w) {
   const WCand &cd = w.cand[r.q];
   const int tid = threadIdx.x, lane = tid & 31, wit = tid >> 5, C = p.C;
   const int hs = (2 * C) | 1;
-  int32_t *s_rows = reinterpret_cast<int32_t *>(smem_raw);
-  int32_t *s_hist = s_rows + w.chunk;                                // [32][hs] (classification)
-  uint8_t *s_lab8 = reinterpret_cast<uint8_t *>(s_hist + 32 * hs);   // [chunk]
+  __shared__ __align__(8) uint64_t s_bar;
+  int32_t *s_hist = reinterpret_cast<int32_t *>(smem_raw) + w.chunk + 8;  // [32][hs] (classification)
+  uint8_t *s_lab8 = reinterpret_cast<uint8_t *>(s_hist + 32 * hs);        // [chunk]
   const int64_t seg = (int64_t)nd.tree * p.n + nd.b + r.j0;
-  for (int32_t j = tid; j < r.cnt; j += WT) {
-    s_rows[j] = p.idx_src[seg + j];
-    if (TASK == TASK_CLS) s_lab8[j] = (uint8_t)p.yc_src[seg + j];
+  if (w.bulk) {
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
   }
+  const int32_t *s_rows = stage_rows(reinterpret_cast<int32_t *>(smem_raw), p.idx_src + seg, r.cnt, &s_bar, w.bulk, tid);
+  if (TASK == TASK_CLS)
+    for (int32_t j = tid; j < r.cnt; j += WT) s_lab8[j] = (uint8_t)p.yc_src[seg + j];
   if (TASK == TASK_CLS)
     for (int t = tid; t < nb * hs; t += WT) s_hist[t] = 0;
   uint32_t act = 0u, nanact = 0u;  // candidates to count: scored ones / those with NaNs
@@ -682,6 +712,7 @@ __global__ void __launch_bounds__(WT) k_wide_pass2(P p, WState w) {
       s_redi[1] = (int32_t)nanact;
     }
   }
+  if (w.bulk) mbar_wait(&s_bar, 0);
   __syncthreads();
   act = (uint32_t)s_redi[0];
   nanact = (uint32_t)s_redi[1];
@@ -1226,11 +1257,15 @@ void wide_level(et_ctx *ctx, const P &p, int32_t count, int64_t wide_rows, const
   w.pending = wb.pending.p;
   w.chunk = chunk;
   w.count = count;
+  {
+    static const bool no_bulk = getenv("ETGPU_NO_BULK") != nullptr && atoi(getenv("ETGPU_NO_BULK")) != 0;
+    w.bulk = no_bulk ? 0 : 1;
+  }
   const unsigned gchunks = (unsigned)max_chunks, gnodes = (unsigned)ceil_div(count, 4);
-  const size_t smem1 = (size_t)chunk * 4;
-  const size_t smem2 = (size_t)chunk * 4 + (TASK == TASK_CLS ? (size_t)32 * ((2 * C) | 1) * 4 + (size_t)chunk : 0);
+  const size_t smem1 = (size_t)chunk * 4 + 32;
+  const size_t smem2 = (size_t)chunk * 4 + 32 + (TASK == TASK_CLS ? (size_t)32 * ((2 * C) | 1) * 4 + (size_t)chunk : 0);
   if (!wb.attr_set) {
-    const int mx1 = WCHUNK_MAX * 4, mx2 = WCHUNK_MAX * 5 + 32 * 65 * 4;
+    const int mx1 = WCHUNK_MAX * 4 + 32, mx2 = WCHUNK_MAX * 5 + 32 + 32 * 65 * 4;
     CUDA_CHECK(cudaFuncSetAttribute(k_wide_pass1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx1));
     CUDA_CHECK(cudaFuncSetAttribute(k_wide_pass1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx1));
     CUDA_CHECK(cudaFuncSetAttribute(k_wide_pass2<TASK_CLS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx2));
