@@ -76,6 +76,11 @@ struct WState {
   int32_t chunk;                // rows per chunk
   int32_t count;
   int32_t bulk;                 // stage a chunk's sample-index segment with one TMA bulk copy (else plain loads)
+  // FP64 tables: pass 1 parks the values it gathers, [chunk][candidate][row of the chunk], so that pass 2 streams
+  // them back (8 bytes per value, coalesced) instead of gathering again (a 32-byte sector per value at depth);
+  // nodes whose batch holds more than park_stride candidates gather twice.  null: off
+  double *park;
+  int32_t park_stride;
 };
 
 // Stages `cnt` sample indices of a node's contiguous segment in shared memory (s_buf: 16-byte aligned, room for
@@ -470,6 +475,7 @@ __global__ void __launch_bounds__(WT) k_wide_pass1(P p, WState w) {
   } else {
     if (w.bulk) mbar_wait(&s_bar, 0);
     __syncthreads();
+    double *park = (w.park && nb <= w.park_stride) ? w.park + (int64_t)blockIdx.x * w.park_stride * w.chunk : nullptr;
     // groups of 4 candidates, four rows per thread and trip: 16 independent gathers in flight
     for (int g0 = 0; g0 < nb; g0 += 4) {
       Col colp[4];
@@ -497,6 +503,13 @@ __global__ void __launch_bounds__(WT) k_wide_pass1(P p, WState w) {
         for (int u2 = 0; u2 < 4; u2++)
 #pragma unroll
           for (int c = 0; c < 4; c++) x[u2][c] = (r4[u2] >= 0) ? col_at(colp[c], r4[u2]) : NAN;
+        if (park) {
+#pragma unroll
+          for (int u2 = 0; u2 < 4; u2++)
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+              if (r4[u2] >= 0 && g0 + c < nb) park[(int64_t)(g0 + c) * w.chunk + j0 + u2 * WT] = x[u2][c];
+        }
 #pragma unroll
         for (int u2 = 0; u2 < 4; u2++) {
 #pragma unroll
@@ -627,7 +640,7 @@ __global__ void __launch_bounds__(128) k_wide_decide(P p, WState w) {
 template <typename LabFn>
 __device__ __forceinline__ void fp64_pass2(const P &p, const int32_t *s_feat, const double *s_cut, const uint32_t act,
                                            int sweep, const int32_t *rr, LabFn lab, int32_t n, int C, int wit, int lane,
-                                           int32_t *s_hist, int hs, int hoff, int nb) {
+                                           int32_t *s_hist, int hs, int hoff, int nb, const double *park, int chunk) {
   int32_t acc[32];
 #pragma unroll
   for (int k = 0; k < 32; k++) acc[k] = 0;
@@ -637,11 +650,20 @@ __device__ __forceinline__ void fp64_pass2(const P &p, const int32_t *s_feat, co
     const int32_t cls = valid ? lab(j) : -1;
     const int32_t row = valid ? rr[j] : 0;
     uint32_t rowbits = 0u;
+    if (park) {  // the values pass 1 gathered: candidate-major, a warp reads 32 consecutive rows of one candidate
 #pragma unroll 8
-    for (int c = 0; c < nb; c++) {
-      const double x = col_at(col_of(p, s_feat[c]), row);
-      const bool in = sweep ? (x != x) : (x < s_cut[c]);
-      rowbits |= (uint32_t)in << c;
+      for (int c = 0; c < nb; c++) {
+        const double x = valid ? park[(int64_t)c * chunk + j] : 0.0;
+        const bool in = sweep ? (x != x) : (x < s_cut[c]);
+        rowbits |= (uint32_t)in << c;
+      }
+    } else {
+#pragma unroll 8
+      for (int c = 0; c < nb; c++) {
+        const double x = col_at(col_of(p, s_feat[c]), row);
+        const bool in = sweep ? (x != x) : (x < s_cut[c]);
+        rowbits |= (uint32_t)in << c;
+      }
     }
     rowbits &= act;
     if (!valid) rowbits = 0u;
@@ -718,6 +740,7 @@ __global__ void __launch_bounds__(WT) k_wide_pass2(P p, WState w) {
   nanact = (uint32_t)s_redi[1];
   __syncthreads();
   const int nsweep = nd.nsweep;
+  const double *park = (!CODED && w.park && nb <= w.park_stride) ? w.park + (int64_t)blockIdx.x * w.park_stride * w.chunk : nullptr;
   if (TASK == TASK_CLS) {
     auto lab = [&](int32_t j) -> int32_t { return (int32_t)s_lab8[j]; };
     for (int sweep = 0; sweep < nsweep; sweep++) {
@@ -737,7 +760,8 @@ __global__ void __launch_bounds__(WT) k_wide_pass2(P p, WState w) {
           coded_pass2<8, WT>(p.C8, s_coloff, s_K4, s_t4, s_e4, sweep, s_rows, lab, r.cnt, C, wit, lane, s_hist, hs, hoff, nb,
                              nullptr);
       } else {
-        fp64_pass2(p, s_feat, s_cut, sweep ? nanact : act, sweep, s_rows, lab, r.cnt, C, wit, lane, s_hist, hs, hoff, nb);
+        fp64_pass2(p, s_feat, s_cut, sweep ? nanact : act, sweep, s_rows, lab, r.cnt, C, wit, lane, s_hist, hs, hoff, nb,
+                   park, w.chunk);
       }
     }
     __syncthreads();
@@ -788,10 +812,18 @@ __global__ void __launch_bounds__(WT) k_wide_pass2(P p, WState w) {
             r4[u2] = (j < r.cnt) ? s_rows[j] : -1;
             yd[u2] = (j < r.cnt) ? ET_SUB(yy[j], mu) : 0.0;
           }
+          if (park) {
 #pragma unroll
-          for (int u2 = 0; u2 < 4; u2++)
+            for (int u2 = 0; u2 < 4; u2++)
 #pragma unroll
-            for (int c = 0; c < 4; c++) x[u2][c] = (r4[u2] >= 0) ? col_at(colp[c], r4[u2]) : 0.0;
+              for (int c = 0; c < 4; c++)
+                x[u2][c] = (r4[u2] >= 0 && g0 + c < nb) ? park[(int64_t)(g0 + c) * w.chunk + j0 + u2 * WT] : 0.0;
+          } else {
+#pragma unroll
+            for (int u2 = 0; u2 < 4; u2++)
+#pragma unroll
+              for (int c = 0; c < 4; c++) x[u2][c] = (r4[u2] >= 0) ? col_at(colp[c], r4[u2]) : 0.0;
+          }
 #pragma unroll
           for (int u2 = 0; u2 < 4; u2++) {
             const double yd2 = ET_MUL(yd[u2], yd[u2]);
@@ -1199,7 +1231,7 @@ struct WideBufs {
   DevBuf<int64_t> chunk0;
   DevBuf<int32_t> hist, besthl, cnt_left;
   DevBuf<uint32_t> cmask, taken, bits;
-  DevBuf<double> part, ysum;
+  DevBuf<double> part, ysum, park;
   DevBuf<unsigned long long> pending;
   bool attr_set = false;
 };
@@ -1242,6 +1274,19 @@ void wide_level(et_ctx *ctx, const P &p, int32_t count, int64_t wide_rows, const
     wb.ysum.ensure((size_t)max_chunks * 2);
   }
   wb.pending.ensure(2);
+  // parked values of pass 1 (FP64 tables): [chunks][stride candidates][chunk rows]; kept within a third of the free HBM
+  int park_stride = 0;
+  if (!coded) {
+    static const bool no_park = getenv("ETGPU_NO_PARK") != nullptr && atoi(getenv("ETGPU_NO_PARK")) != 0;
+    park_stride = no_park ? 0 : std::min(32, ((p.k + std::max(2, p.k / 4)) + 3) / 4 * 4);
+    const size_t need = (size_t)max_chunks * (size_t)park_stride * (size_t)chunk;
+    if (park_stride > 0 && need > wb.park.cap) {
+      size_t fr = 0, tot = 0;
+      cudaMemGetInfo(&fr, &tot);
+      if (need * sizeof(double) > (fr + wb.park.cap * sizeof(double)) / 3) park_stride = 0;
+    }
+    if (park_stride > 0) wb.park.ensure(need, 1.0);
+  }
   WState w;
   w.node = wb.node.p;
   w.cand = wb.cand.p;
@@ -1255,6 +1300,8 @@ void wide_level(et_ctx *ctx, const P &p, int32_t count, int64_t wide_rows, const
   w.cnt_left = wb.cnt_left.p;
   w.bits = wb.bits.p;
   w.pending = wb.pending.p;
+  w.park = park_stride > 0 ? wb.park.p : nullptr;
+  w.park_stride = park_stride;
   w.chunk = chunk;
   w.count = count;
   {
