@@ -134,6 +134,60 @@ def gen_sparse(n, d, density, seed):
     return colptr, rows, vals, y
 
 
+def gen_sparse_gpu(torch, n, d, density, seed):
+    """The same law as gen_sparse, drawn on the GPU (100M entries in a fraction of a second); returns host arrays."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    nnz0 = int(n * d * density)
+    key = torch.randint(0, n * d, (nnz0,), device="cuda", generator=g, dtype=torch.int64)  # column * n + row
+    key = torch.unique(key)  # sorted, duplicates dropped (a Binomial(n, density) count per column in the limit)
+    cols = torch.div(key, n, rounding_mode="floor")
+    rows = (key - cols * n).to(torch.int32)
+    colptr = torch.zeros(d + 1, dtype=torch.int64, device="cuda")
+    colptr[1:] = torch.cumsum(torch.bincount(cols, minlength=d), 0)
+    vals = torch.randn(len(key), device="cuda", generator=g, dtype=torch.float64).abs() + 0.1
+    info = torch.randperm(d, device="cuda", generator=g)[:50]
+    sgn = (torch.randint(0, 2, (50,), device="cuda", generator=g) * 2 - 1).to(torch.float64)
+    w = torch.zeros(d, dtype=torch.float64, device="cuda")
+    w[info] = sgn
+    score = torch.zeros(n, dtype=torch.float64, device="cuda")
+    score.index_add_(0, rows.to(torch.int64), vals * w[cols])
+    score += 0.05 * torch.randn(n, device="cuda", generator=g, dtype=torch.float64)
+    y = (score > score.median()).to(torch.int32)
+    out = tuple(t.cpu().numpy() for t in (colptr, rows, vals, y))
+    del key, cols, rows, vals, score, w
+    torch.cuda.empty_cache()
+    return out
+
+
+def sparse_full_size(et, torch, ctx, trees=2):
+    """BASELINE configs[3] at its full size, kept sparse in HBM (et_data_csc: 12 bytes per stored entry; the dense
+    form would be 80 GB): a bounded number of trees, GPU only (the CPU port needs the dense matrix)."""
+    cfg = CONFIGS["sparse"]
+    n, d = cfg["n"], cfg["d"]
+    colptr, rowidx, vals, y = gen_sparse_gpu(torch, n, d, cfg["density"], cfg["seed"])
+    free0, _ = torch.cuda.mem_get_info()
+    t0 = time.perf_counter()
+    dd = et.DeviceData.from_csc(colptr, rowidx, vals, n, d, ctx)
+    dd.set_target_classification(y, cfg["C"])
+    t1 = time.perf_counter()
+    f = et.buildForestClassification(dd, None, None, cfg["C"], cfg["n_min"], cfg["k"], trees, 8, seed=1, ctx=ctx)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    free1, _ = torch.cuda.mem_get_info()
+    ent = {"workload": cfg["name"], "rows": n, "features": d, "stored_entries": int(len(vals)), "trees": trees,
+           "k": cfg["k"], "resident": "CSC (sparse), values found by binary search among a column's stored rows",
+           "table_bytes_hbm": int(len(vals)) * 12 + (d + 1) * 8, "dense_bytes": n * d * 8,
+           "hbm_in_use_after_build_bytes": int(free0 - free1),
+           "upload_s": t1 - t0, "build": {"value": trees / (t2 - t1), "unit": "trees/s", "ms_per_step": 1e3 * (t2 - t1),
+                                          "steps": 1, "warmup": 0, "note": "first build of the context (allocations inside)"},
+           "stats_per_step": {k: f.stats[k] for k in ("nodes", "levels", "v_mm", "draws", "const_hits")}}
+    f.free()
+    dd.free()
+    torch.cuda.empty_cache()
+    return ent
+
+
 def csc_to_dense(colptr, rowidx, vals, n, d):
     x = np.zeros((n, d))
     cols = np.repeat(np.arange(d), np.diff(colptr))
@@ -587,19 +641,25 @@ def run_extra(key, args, et, torch, ctx, stream):
     if key == "sparse":
         cpu_table = (csc_to_dense(*b.csc, cfg["n"], cfg["d"]), b.y, " (dense expansion of the CSC table)") \
             if cfg["n"] * cfg["d"] <= 1_000_000_000 else None
-    r = measure(b, 1, 1, want_e2e=(key != "large"), want_cpu=True, cpu_table=cpu_table)
+    steps = 2 if key == "reg" else 1
+    r = measure(b, steps, 1, want_e2e=(key != "large"), want_cpu=True, cpu_table=cpu_table)
     ent = {"workload": full_cfg["name"],
            "bounded": {k: {"config": v[0], "run": v[1]} for k, v in cut.items()} or None,
            "rows": cfg["n"], "features": cfg["d"], "trees": cfg["trees"], "k": cfg["k"], "n_min": cfg["n_min"],
-           "build": {"value": r["value"], "unit": "trees/s", "ms_per_step": r["ms_build"], "steps": 1, "warmup": 1},
+           "build": {"value": r["value"], "unit": "trees/s", "ms_per_step": r["ms_build"] / steps, "steps": steps, "warmup": 1},
            "e2e": r["e2e"] if r["e2e"] else {"value": None, "note": "table generated on the device (20.5 GB): no host copy to upload"},
            "roofline": r["roofline"], "predict": r["predict"], "cpu_baseline": r.get("cpu_baseline"),
-           "stats_per_step": stats_block(r, 1), "wall_s": None}
+           "stats_per_step": stats_block(r, steps), "wall_s": None}
     for o in (r["full"], r["shard"]):
         o.free()
     b.dd.free()
     del b
     torch.cuda.empty_cache()
+    if key == "sparse":
+        try:
+            ent["full_size"] = sparse_full_size(et, torch, ctx)
+        except Exception as e:
+            ent["full_size"] = {"error": repr(e)}
     ent["wall_s"] = time.perf_counter() - t0
     return ent
 
@@ -648,7 +708,8 @@ def main():
         D.init_comm(ctx, rank, world)  # NCCL communicator INSIDE the library (gather of trees, predict all-reduce)
 
     b = Bench(cfg, args, et, torch, ctx, stream, rank, world, D)
-    r = measure(b, args.steps, args.warmup, want_e2e=True, want_cpu=not args.no_cpu_baseline, clocks_device=local)
+    has_host_table = b.x_host is not None or b.csc is not None
+    r = measure(b, args.steps, args.warmup, want_e2e=has_host_table, want_cpu=not args.no_cpu_baseline, clocks_device=local)
     n, d, m = cfg["n"], cfg["d"], cfg["trees"]
     launches = r["agg"]["launches"]
     line = {
@@ -663,7 +724,8 @@ def main():
                    "l2": "no flush: the working set of a step (sample-index / label ping-pong buffers %.0f MB + "
                          "byte-coded table 2 x %.0f MB + FP64 table %.0f MB) is larger than the 126 MB L2"
                          % (2 * 8 * len(b.ids) * n / 1e6, n * d / 1e6, 8.0 * n * d / 1e6)},
-        "e2e": r["e2e"],
+        "e2e": r["e2e"] if r["e2e"] else {"value": None, "unit": "trees/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                          "note": "table generated on the device: no host copy to upload"},
         "gpu_launches": int(launches),
         "clocks": r["clocks"],
         "roofline": r["roofline"],

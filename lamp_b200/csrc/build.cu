@@ -226,7 +226,9 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
     lc.smem_mid = (size_t)make_lay(task, MID_TEAM, C, NB, W, replay, true).bytes;
     lc.smem_cta = (size_t)make_lay(task, CBIG_TEAM, C, NB, W, replay, true).bytes;
   }
-  if (!lc.coded) lc.smem_lane[0] = (size_t)lane_smem_bytes(task, C, W, replay, 1, 8);
+  // FP64 tables: k_lane parks k + slack values per row instead of 32 (more warps per SM; batches are capped to it)
+  const int lane_nb = std::min(32, (a.k + std::max(2, a.k / 4) + 3) / 4 * 4);
+  if (!lc.coded) lc.smem_lane[0] = (size_t)lane_smem_bytes(task, C, W, replay, 1, 8, lane_nb);
   if (lc.smem_lane[0] * LANE_WARPS > 200 * 1024)
     ET_FAIL(ET_EUNSUPPORTED, "numClasses=%d / %d features need more shared memory per node than one SM has", C, d);
   // Nodes above wide_min rows are cut into chunks of rows, one CTA per chunk (wide.cu): unweighted classification
@@ -384,6 +386,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       if (const char *env = getenv("ETGPU_NC_MAX")) p.nc_max = std::max(0, atoi(env));
       p.XR = D->xr;
       p.xr_stride = (int32_t)D->rsd;
+      p.lane_nb = lane_nb;
       p.csc_colptr = D->csc_colptr;
       p.csc_row = D->csc_row;
       p.csc_val = D->csc_val;

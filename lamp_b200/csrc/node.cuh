@@ -1205,11 +1205,13 @@ constexpr int LANE_WARPS = 4;
 #define LANE_SMALL_CTAS 8
 #endif
 
-__host__ __device__ inline int lane_smem_bytes(int task, int C, int W, bool replay, int NW, int vbytes) {
+// lnb = candidates per batch whose values are parked (32 on byte-coded tables; on FP64 tables k plus some slack,
+// so that the 8-byte values of a 32-row node take k-ish instead of 32 slots per row and more warps fit an SM)
+__host__ __device__ inline int lane_smem_bytes(int task, int C, int W, bool replay, int NW, int vbytes, int lnb = 32) {
   int o = 0;
   o += (task == TASK_CLS) ? 0 : 32 * NW * 8;      // s_y    regression target / weight, by position
   o += (task == TASK_REG) ? 0 : C * 8;            // s_dist
-  o += 32 * NW * 32 * vbytes;                     // s_x    parked values [position][lane]
+  o += 32 * NW * lnb * vbytes;                    // s_x    parked values [position][lane < lnb]
   o += 2 * NW * 32 * 4;                           // s_lt, s_nn  side bitmasks [word][lane]
   o += NW * 4;                                    // s_best winner's bitmask
   o += (task == TASK_REG) ? 0 : C * NW * 4;       // s_cm   per class, bitmask over the positions
@@ -1339,11 +1341,12 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? LANE_SMALL_CTAS : 4) 
   const int q = blockIdx.x * LANE_WARPS + tic;
   if (q >= qcount) return;
   const int C = p.C, W = p.W;
-  unsigned char *sm = smem_raw + (size_t)tic * lane_smem_bytes(TASK, C, W, p.replay != 0, NW, (int)sizeof(VT));
+  const int LNB = CODED ? 32 : p.lane_nb;
+  unsigned char *sm = smem_raw + (size_t)tic * lane_smem_bytes(TASK, C, W, p.replay != 0, NW, (int)sizeof(VT), LNB);
   double *s_y = reinterpret_cast<double *>(sm);
   double *s_dist = s_y + ((TASK == TASK_CLS) ? 0 : 32 * NW);
   VT *s_x = reinterpret_cast<VT *>(s_dist + ((TASK == TASK_REG) ? 0 : C));
-  uint32_t *s_lt = reinterpret_cast<uint32_t *>(s_x + 32 * NW * 32);
+  uint32_t *s_lt = reinterpret_cast<uint32_t *>(s_x + 32 * NW * LNB);
   uint32_t *s_nn = s_lt + NW * 32;
   uint32_t *s_best = s_nn + NW * 32;
   uint32_t *s_cm = s_best + NW;
@@ -1556,7 +1559,7 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? LANE_SMALL_CTAS : 4) 
       int32_t nb;
       const int32_t avail = p.d - nconst - visited;
       if (p.replay) {
-        nb = min(32, tcnt - tpos);
+        nb = min(LNB, tcnt - tpos);
       } else if (use_nc) {
         nb = (min(p.k - visited, avail) > 0) ? 32 : 0;
       } else {
@@ -1572,7 +1575,7 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? LANE_SMALL_CTAS : 4) 
                       : 0;
         else
           extra = (nconst > 0) ? need + 4 : 0;
-        nb = (need > 0) ? min(32, min(avail, need + extra)) : 0;
+        nb = (need > 0) ? min(LNB, min(avail, need + extra)) : 0;
       }
       if (nb <= 0) break;
       // ---- draw: lane == candidate
@@ -1671,7 +1674,7 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? LANE_SMALL_CTAS : 4) 
           mnt = min(mnt, b8 - K);
         } else {
           const double x = act0 ? col_at(dcol, rj) : 0.0;
-          s_x[pos * 32 + lane] = (VT)x;
+          if (lane < LNB) s_x[pos * LNB + lane] = (VT)x;
           if (x < mn) mn = x;
           if (x > mx) mx = x;
           has_nan |= (x != x);
@@ -1748,7 +1751,7 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? LANE_SMALL_CTAS : 4) 
         } else {
 #pragma unroll 8
           for (int jj = 0; jj < cnt; jj++) {
-            const double x = (double)s_x[(j0 + jj) * 32 + lane];
+            const double x = (lane < LNB) ? (double)s_x[(j0 + jj) * LNB + lane] : 0.0;
             lt |= (uint32_t)(x < cut) << jj;
             nn |= (uint32_t)(x != x) << jj;
           }
