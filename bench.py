@@ -357,6 +357,7 @@ class Bench:
         self.ids = D.shard_tree_ids(self.m, rank, world)  # strong scaling: the forest is fixed, its trees are sharded
         self.x_host = self.y = self.csc = self.x_dev = self.x_pred_dev = self.x_pageable = None
         self.pinned = {}
+        self.gathered = world > 1
         self._make_data()
 
     # ---- data -------------------------------------------------------------------------------------------------
@@ -418,8 +419,12 @@ class Bench:
         """Table resident in HBM; N > 1: + the in-library all-gather of the serialized trees."""
         f = self.build(self.dd, None, seed)
         if self.world > 1:
-            full = self.D.gather_forest(self.ctx, f)
-            return f, full, self.ctx.comm_last_ms()
+            # (a forest whose gathered form would not fit next to the tables stays sharded: configs[4] at its full
+            # 2000 trees is ~180 GB of nodes; predict is tree-sharded either way)
+            self.gathered = f.total_nodes * self.world * 24 < 40e9 and self.args.gather != "off"
+            if self.gathered:
+                full = self.D.gather_forest(self.ctx, f)
+                return f, full, self.ctx.comm_last_ms()
         return f, f, 0.0
 
     def export_pinned(self, f):
@@ -675,6 +680,9 @@ def main():
     ap.add_argument("--extra", default="all", help="bounded runs of the other BASELINE configs in the N=1 line: "
                                                    "all | none | comma list of reg,sparse,large")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="auto", choices=["auto", "off"],
+                    help="N > 1: all-gather the serialized trees inside the timed region (auto: unless the gathered "
+                         "forest would not fit in HBM)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     cfg["_main"] = True
@@ -733,7 +741,8 @@ def main():
         "stats_per_step": stats_block(r, args.steps),
     }
     if world > 1:
-        line["collectives"] = {"forest_allgather_ms_per_step": r["gather_ms"] / args.steps,
+        line["collectives"] = {"forest_gathered": bool(b.gathered),
+                               "forest_allgather_ms_per_step": r["gather_ms"] / args.steps,
                                "predict_allreduce_stream_ms_per_step": r["allreduce_ms"] / args.steps,
                                "note": "device time, max over ranks; the all-reduce runs in row chunks on its own stream "
                                        "overlapped with the traversal (the figure is that stream's span)"}

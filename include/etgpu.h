@@ -53,7 +53,7 @@ int et_init(int32_t device, et_ctx **out);
  *                        (every GPU holds a replica of the table); targets / weights go to every GPU
  *   et_build_*           tree t of the forest is built by GPU t mod G (a tree's random stream depends only on
  *                        (seed, tree id): the forest equals the one a single GPU builds); the serialized trees
- *                        are all-gathered (ncclAllGather of sizes, grouped ncclBroadcast of the packed nodes),
+ *                        are all-gathered (ncclAllGather of the sizes, then of the packed nodes over padded slots),
  *                        so every GPU -- and the host, through et_forest_export* -- holds the whole forest
  *   et_predict_*         trees stay sharded: every GPU traverses all rows for its trees, the per-row partial
  *                        sums are all-reduced (ncclAllReduce, FP64 sum) and divided by m once.  The sum is

@@ -550,6 +550,72 @@ __global__ void k_csc_scatter(const int64_t *__restrict__ colptr, const int32_t 
   x[(int64_t)(c0 + lo) * ld + rowidx[e - e0]] = val[e - e0];
 }
 
+// row-major index of a sparse-resident table: entries per row, exclusive scan, fill through per-row cursors
+__global__ void k_csr_count(const int32_t *__restrict__ rowidx, int64_t nnz, unsigned long long *__restrict__ cnt) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nnz) atomicAdd(&cnt[rowidx[e]], 1ull);
+}
+__global__ void __launch_bounds__(1024) k_csr_scan(unsigned long long *cnt, int64_t n, int64_t *ptr) {
+  // one CTA: every thread sums a contiguous slice, the slices are scanned through shared memory
+  __shared__ unsigned long long s_part[1024];
+  const int64_t per = (n + 1023) / 1024, a = (int64_t)threadIdx.x * per, b = min(n, a + per);
+  unsigned long long s = 0;
+  for (int64_t i = a; i < b; i++) s += cnt[i];
+  s_part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (int t = 0; t < 1024; t++) {
+      const unsigned long long v = s_part[t];
+      s_part[t] = run;
+      run += v;
+    }
+    ptr[n] = (int64_t)run;
+  }
+  __syncthreads();
+  unsigned long long run = s_part[threadIdx.x];
+  for (int64_t i = a; i < b; i++) {
+    const unsigned long long v = cnt[i];
+    ptr[i] = (int64_t)run;
+    cnt[i] = run;  // becomes the row's fill cursor
+    run += v;
+  }
+}
+__global__ void k_csr_fill(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx, int32_t d, int64_t nnz,
+                           unsigned long long *__restrict__ cursor, int32_t *__restrict__ csr_col) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  int lo = 0, hi = d;  // the column of entry e: last c with colptr[c] <= e
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (colptr[mid] <= e)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  csr_col[atomicAdd(&cursor[rowidx[e]], 1ull)] = lo;
+}
+
+// the row-major index (which features a row stores) of a sparse-resident table: small free-running nodes mark every
+// feature none of their rows stores as constant up front (build.cuh sparse_mark_constant)
+void et_data_build_csr(et_ctx *ctx, et_data *D) {
+  const int64_t n = D->n, nnz = D->csc_nnz;
+  unsigned long long *d_cnt = nullptr;
+  CUDA_CHECK(cudaMalloc((void **)&D->csr_ptr, ((size_t)n + 1) * sizeof(int64_t)));
+  CUDA_CHECK(cudaMalloc((void **)&D->csr_col, std::max<size_t>(1, (size_t)nnz) * sizeof(int32_t)));
+  CUDA_CHECK(cudaMalloc((void **)&d_cnt, std::max<size_t>(1, (size_t)n) * sizeof(unsigned long long)));
+  cudaMemsetAsync(d_cnt, 0, std::max<size_t>(1, (size_t)n) * sizeof(unsigned long long), ctx->stream);
+  if (nnz > 0) k_csr_count<<<(unsigned)ceil_div(nnz, 256), 256, 0, ctx->stream>>>(D->csc_row, nnz, d_cnt);
+  k_csr_scan<<<1, 1024, 0, ctx->stream>>>(d_cnt, n, D->csr_ptr);
+  if (nnz > 0)
+    k_csr_fill<<<(unsigned)ceil_div(nnz, 256), 256, 0, ctx->stream>>>(D->csc_colptr, D->csc_row, D->d, nnz, d_cnt, D->csr_col);
+  ctx->launches += 3;
+  cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_cnt);
+  CUDA_CHECK(e2);
+  CUDA_CHECK(cudaGetLastError());
+}
+
 // CSC input (BASELINE configs[3]).  The stored entries of a column are kept in ascending row order without
 // duplicates (a row listed twice keeps the LATER entry; unsorted input is sorted on the host first), so a kernel
 // finds the value of (row, column) by binary search and everything not stored is an implicit 0.0 with dense
@@ -631,11 +697,15 @@ extern "C" int et_data_csc(et_ctx *ctx, const int64_t *colptr, const int32_t *ro
         CUDA_CHECK(cudaMemcpyAsync(D->csc_row, rowidx, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
         CUDA_CHECK(cudaMemcpyAsync(D->csc_val, val, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
       }
-      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      et_data_build_csr(ctx, D.get());
     } catch (...) {
       cudaFree(D->csc_colptr);
       cudaFree(D->csc_row);
       cudaFree(D->csc_val);
+      cudaFree(D->csr_ptr);
+      cudaFree(D->csr_col);
+      D->csc_colptr = nullptr;
+      D->csr_ptr = nullptr;
       throw;
     }
     *out = D.release();
@@ -803,6 +873,8 @@ extern "C" void et_data_free(et_data *D) {
     if (D->csc_colptr) cudaFree(D->csc_colptr);
     if (D->csc_row) cudaFree(D->csc_row);
     if (D->csc_val) cudaFree(D->csc_val);
+    if (D->csr_ptr) cudaFree(D->csr_ptr);
+    if (D->csr_col) cudaFree(D->csr_col);
     if (D->y_cls) cudaFree(D->y_cls);
     if (D->y_reg) cudaFree(D->y_reg);
     if (D->w) cudaFree(D->w);

@@ -248,6 +248,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
     // Regression: the one-CTA team of a large node holds an SM alone (512 threads, moment sums), the chunked path
     // was measured faster at every level of the 1M-row table, so it takes every node above NM_MAX rows.
     if (task == TASK_REG) return NM_MAX;
+    if (D->csc_row) return NM_MAX;  // sparse-resident table: the chunked path walks stored entries instead of rows
     return (int32_t)std::min<int64_t>(0x7fffffff, std::max<int64_t>(16384, big_rows / (4 * cta_slots)));
   };
   if (task == TASK_CLS)
@@ -376,6 +377,15 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       p.cls_max[Q_WARP] = NW_MAX;
       p.cls_max[Q_MID] = NM_MAX;
       p.cls_max[Q_CTA] = wide_min_for(n > NM_MAX ? (int64_t)Bt * n : 0);
+      // Sparse-resident table: every node above sparse_wide_min rows takes the chunked path, where a chunk walks the
+      // stored entries of a candidate's column (wide.cu) -- the one-team kernels would search the column once per
+      // (row, candidate) and a single 2048-row node held a level for milliseconds.
+      int32_t sparse_wide_min = 0;
+      if (D->csc_row && lc.wide) {
+        sparse_wide_min = NM_MAX;
+        if (const char *env = getenv("ETGPU_SPARSE_WIDE_MIN")) sparse_wide_min = std::max(NT_MAX, atoi(env));
+        for (int q = Q_LANE0 + 1; q <= Q_CTA; q++) p.cls_max[q] = std::min(p.cls_max[q], sparse_wide_min);
+      }
       if (a.best_split) {  // bestSplit: one kernel family (best.cu), every node in queue Q_CTA
         for (int q = 0; q < Q_CTA; q++) p.cls_max[q] = 0;
         p.cls_max[Q_CTA] = 0x7fffffff;
@@ -390,6 +400,8 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       p.csc_colptr = D->csc_colptr;
       p.csc_row = D->csc_row;
       p.csc_val = D->csc_val;
+      p.csr_ptr = D->csr_ptr;
+      p.csr_col = D->csr_col;
       p.tr = trace;
       int srcb = 0, cl = 0;  // cl: frontier slot of the current level
       int32_t F = Bt;
@@ -452,7 +464,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
         p.o = ws.pool.view();
         p.scratch = ws.scratch.p;
         p.node_base_next = (int32_t)n_nodes;
-        if (!a.best_split) p.cls_max[Q_CTA] = wide_min_for(big_rows);  // the bound the children are classed by
+        if (!a.best_split) p.cls_max[Q_CTA] = sparse_wide_min ? std::min(sparse_wide_min, wide_min_for(big_rows)) : wide_min_for(big_rows);  // the bound the children are classed by
         if (a.best_split) {
           const int e0 = evt.rec(st);
           if (task == TASK_CLS)

@@ -201,6 +201,9 @@ struct P {
   const int64_t *csc_colptr;
   const int32_t *csc_row;
   const double *csc_val;
+  // ... and its row-major index (which features a row stores): csr_col[csr_ptr[r] .. csr_ptr[r + 1])
+  const int64_t *csr_ptr;
+  const int32_t *csr_col;
 };
 
 // Column f of the table: dense FP64 values, or the stored entries of a CSC column (everything not stored is 0.0
@@ -255,6 +258,35 @@ __device__ __forceinline__ void team_sync() {
   else
     __syncthreads();
 }
+
+// Sparse-resident table, free-running mode: a feature that none of the node's rows stores is all-zero in the
+// node, hence constant (pkg:236) -- marked known-constant up front from the rows' stored features (CSR index)
+// instead of being found by drawing it.  On a 1 % dense table a 10-row node stores ~1000 of 10000 features: the
+// scored candidates of the reference are a uniform sample without replacement of the varying features either way
+// (draws that hit a constant feature are discarded, pkg:236-239), so the split has the same distribution and the
+// ~90 % of draws that would hit all-zero features are never made.  `rows` = the node's rows (shared or global).
+template <int TEAM>
+__device__ __forceinline__ void sparse_mark_constant(const P &p, const int32_t *rows, int32_t n, uint32_t *s_const,
+                                                     uint32_t *s_taken, int W, int tid) {
+  for (int w = tid; w < W; w += TEAM) s_taken[w] = 0xffffffffu;
+  team_sync<TEAM>();
+  for (int32_t j = 0; j < n; j++) {
+    const int32_t r = rows[j];
+    const int64_t a = __ldg(p.csr_ptr + r), e = __ldg(p.csr_ptr + r + 1);
+    for (int64_t t = a + tid; t < e; t += TEAM) {
+      const int32_t f = __ldg(p.csr_col + t);
+      atomicAnd(&s_taken[f >> 5], ~(1u << (f & 31)));
+    }
+  }
+  team_sync<TEAM>();
+  for (int w = tid; w < W; w += TEAM) {
+    const uint32_t v = s_taken[w] | s_const[w];  // (+ what the path from the root already excluded)
+    s_const[w] = v;
+    s_taken[w] = v;
+  }
+  team_sync<TEAM>();
+}
+
 
 // min / max / any over the team; result valid in every thread
 template <int TEAM>

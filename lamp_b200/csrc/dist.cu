@@ -86,21 +86,22 @@ void ensure_comm_stream(et_ctx *ctx) {
   if (!ctx->ev_comm) CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
 }
 
-// device scratch freed on scope exit
+// device scratch from the context's block cache (no cudaMalloc / cudaFree in the steady state: a gather per build
+// would otherwise pay several synchronising frees), given back on scope exit -- the caller has synchronised by then
 struct DevTmp {
-  std::vector<void *> p;
+  et_ctx *ctx;
+  std::vector<std::pair<void *, size_t>> p;
+  explicit DevTmp(et_ctx *c) : ctx(c) {}
   template <typename T>
   T *alloc(size_t n) {
-    T *d = nullptr;
-    if (cudaMalloc((void **)&d, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) {
-      cudaGetLastError();
-      ET_FAIL(ET_ENOMEM, "device allocation of %zu bytes failed", n * sizeof(T));
-    }
-    p.push_back(d);
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    T *d = static_cast<T *>(et_dev_alloc(ctx, bytes));
+    if (!d) ET_FAIL(ET_ENOMEM, "device allocation of %zu bytes failed", bytes);
+    p.push_back({d, bytes});
     return d;
   }
   ~DevTmp() {
-    for (void *d : p) cudaFree(d);
+    for (auto &q : p) et_dev_free(ctx, q.first, q.second);
   }
 };
 
@@ -150,7 +151,7 @@ et_forest *forest_allgather_rank(et_ctx *ctx, et_forest *shard) {
   const int world = ctx->world, rank = ctx->rank;
   cudaStream_t st = ctx->stream;
   const int lw = shard->leaf_width;
-  DevTmp tmp;
+  DevTmp tmp(ctx);
   EventPair ev;
   // ---- sizes: (trees, nodes, leaves, d_min) of every rank
   int64_t hdr[4] = {shard->m, shard->total_nodes, shard->total_leaves, shard->d_min};
@@ -161,17 +162,22 @@ et_forest *forest_allgather_rank(et_ctx *ctx, et_forest *shard) {
   std::vector<int64_t> all((size_t)4 * world);
   CUDA_CHECK(cudaMemcpyAsync(all.data(), d_hdr, all.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
-  int64_t max_m = 0, m_tot = 0, nodes_tot = 0, leaves_tot = 0, d_min = 0;
-  std::vector<int64_t> node0((size_t)world + 1, 0), leaf0((size_t)world + 1, 0);
+  int64_t max_m = 0, m_tot = 0, nodes_tot = 0, leaves_tot = 0, d_min = 0, max_nodes = 0, max_leaves = 0;
   for (int r = 0; r < world; r++) {
     max_m = std::max(max_m, all[(size_t)4 * r]);
     m_tot += all[(size_t)4 * r];
-    node0[(size_t)r + 1] = node0[(size_t)r] + all[(size_t)4 * r + 1];
-    leaf0[(size_t)r + 1] = leaf0[(size_t)r] + all[(size_t)4 * r + 2];
+    nodes_tot += all[(size_t)4 * r + 1];
+    leaves_tot += all[(size_t)4 * r + 2];
+    max_nodes = std::max(max_nodes, all[(size_t)4 * r + 1]);
+    max_leaves = std::max(max_leaves, all[(size_t)4 * r + 2]);
     d_min = std::max(d_min, all[(size_t)4 * r + 3]);
   }
-  nodes_tot = node0[(size_t)world];
-  leaves_tot = leaf0[(size_t)world];
+  // rank r's nodes / leaves land at slot r of the staging buffers (slots padded to the largest shard)
+  std::vector<int64_t> node0((size_t)world + 1, 0), leaf0((size_t)world + 1, 0);
+  for (int r = 0; r <= world; r++) {
+    node0[(size_t)r] = (int64_t)r * max_nodes;
+    leaf0[(size_t)r] = (int64_t)r * max_leaves;
+  }
   if (m_tot > 0x7fffffff) ET_FAIL(ET_EUNSUPPORTED, "gathered forest exceeds 2^31 trees");
   // ---- per tree: (order key, nodes), padded to the largest shard
   std::vector<int64_t> meta((size_t)2 * std::max<int64_t>(max_m, 1), 0);
@@ -184,16 +190,20 @@ et_forest *forest_allgather_rank(et_ctx *ctx, et_forest *shard) {
   NCCL_CHECK(N.AllGather(d_meta + meta.size() * rank, d_meta, meta.size(), ncclInt64, comm, st));
   std::vector<int64_t> all_meta(meta.size() * world);
   CUDA_CHECK(cudaMemcpyAsync(all_meta.data(), d_meta, all_meta.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  // ---- the packed nodes and leaf tables of every rank, rank-major (all-gather-v = one broadcast per rank, grouped)
-  PNode *s_nodes = tmp.alloc<PNode>((size_t)nodes_tot);
-  double *s_leaves = tmp.alloc<double>((size_t)leaves_tot * lw);
-  NCCL_CHECK(N.GroupStart());
-  for (int r = 0; r < world; r++) {
-    const size_t nb = (size_t)all[(size_t)4 * r + 1] * sizeof(PNode), lb = (size_t)all[(size_t)4 * r + 2] * lw * sizeof(double);
-    if (nb) NCCL_CHECK(N.Broadcast(r == rank ? (const void *)shard->d_nodes : (const void *)(s_nodes + node0[(size_t)r]), s_nodes + node0[(size_t)r], nb, ncclChar, r, comm, st));
-    if (lb) NCCL_CHECK(N.Broadcast(r == rank ? (const void *)shard->d_leaf : (const void *)(s_leaves + leaf0[(size_t)r] * lw), s_leaves + leaf0[(size_t)r] * lw, lb, ncclChar, r, comm, st));
-  }
-  NCCL_CHECK(N.GroupEnd());
+  // ---- the packed 16-byte nodes and the leaf tables of every rank: two in-place all-gathers over padded slots
+  PNode *s_nodes = tmp.alloc<PNode>((size_t)world * (size_t)std::max<int64_t>(max_nodes, 1));
+  double *s_leaves = tmp.alloc<double>((size_t)world * (size_t)std::max<int64_t>(max_leaves, 1) * lw);
+  if (shard->total_nodes)
+    CUDA_CHECK(cudaMemcpyAsync(s_nodes + node0[(size_t)rank], shard->d_nodes, (size_t)shard->total_nodes * sizeof(PNode),
+                               cudaMemcpyDeviceToDevice, st));
+  if (shard->total_leaves)
+    CUDA_CHECK(cudaMemcpyAsync(s_leaves + leaf0[(size_t)rank] * lw, shard->d_leaf,
+                               (size_t)shard->total_leaves * lw * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (max_nodes)
+    NCCL_CHECK(N.AllGather(s_nodes + node0[(size_t)rank], s_nodes, (size_t)max_nodes * sizeof(PNode), ncclChar, comm, st));
+  if (max_leaves)
+    NCCL_CHECK(N.AllGather(s_leaves + leaf0[(size_t)rank] * lw, s_leaves, (size_t)max_leaves * lw * sizeof(double), ncclChar,
+                           comm, st));
   CUDA_CHECK(cudaEventRecord(ev.b, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
   // ---- plan: trees in order of their key
@@ -299,16 +309,50 @@ et_data *data_broadcast_rank(et_ctx *ctx, et_data *data, int32_t root) {
   NcclApi &N = nccl();
   ncclComm_t comm = comm_of(ctx);
   cudaStream_t st = ctx->stream;
-  DevTmp tmp;
-  int64_t hdr[2] = {data ? data->n : 0, data ? data->d : 0};
-  int64_t *d_hdr = tmp.alloc<int64_t>(2);
+  DevTmp tmp(ctx);
+  int64_t hdr[3] = {data ? data->n : 0, data ? data->d : 0, (data && !data->x) ? data->csc_nnz : -1};  // nnz < 0: dense
+  int64_t *d_hdr = tmp.alloc<int64_t>(3);
   if (ctx->rank == root) {
     if (!data) ET_FAIL(ET_EINVAL, "et_data_broadcast: the root rank must pass its table");
     CUDA_CHECK(cudaMemcpyAsync(d_hdr, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
   }
-  NCCL_CHECK(N.Broadcast(d_hdr, d_hdr, 2, ncclInt64, root, comm, st));
+  NCCL_CHECK(N.Broadcast(d_hdr, d_hdr, 3, ncclInt64, root, comm, st));
   CUDA_CHECK(cudaMemcpyAsync(hdr, d_hdr, sizeof(hdr), cudaMemcpyDeviceToHost, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
+  if (hdr[2] >= 0) {
+    // a table kept sparse: the three CSC arrays travel, the row-major index is rebuilt locally
+    if (ctx->rank == root) {
+      if (hdr[1] > 0) NCCL_CHECK(N.Broadcast(data->csc_colptr, data->csc_colptr, (size_t)(hdr[1] + 1) * 8, ncclChar, root, comm, st));
+      if (hdr[2] > 0) {
+        NCCL_CHECK(N.Broadcast(data->csc_row, data->csc_row, (size_t)hdr[2] * 4, ncclChar, root, comm, st));
+        NCCL_CHECK(N.Broadcast(data->csc_val, data->csc_val, (size_t)hdr[2] * 8, ncclChar, root, comm, st));
+      }
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      return data;
+    }
+    et_data *S = new et_data();
+    S->ctx = ctx;
+    S->n = hdr[0];
+    S->d = (int32_t)hdr[1];
+    S->ld = ((hdr[0] + 15) / 16) * 16;
+    S->coded = -1;
+    S->csc_nnz = hdr[2];
+    try {
+      CUDA_CHECK(cudaMalloc((void **)&S->csc_colptr, ((size_t)hdr[1] + 1) * sizeof(int64_t)));
+      CUDA_CHECK(cudaMalloc((void **)&S->csc_row, std::max<size_t>(1, (size_t)hdr[2]) * sizeof(int32_t)));
+      CUDA_CHECK(cudaMalloc((void **)&S->csc_val, std::max<size_t>(1, (size_t)hdr[2]) * sizeof(double)));
+      if (hdr[1] > 0) NCCL_CHECK(N.Broadcast(S->csc_colptr, S->csc_colptr, (size_t)(hdr[1] + 1) * 8, ncclChar, root, comm, st));
+      if (hdr[2] > 0) {
+        NCCL_CHECK(N.Broadcast(S->csc_row, S->csc_row, (size_t)hdr[2] * 4, ncclChar, root, comm, st));
+        NCCL_CHECK(N.Broadcast(S->csc_val, S->csc_val, (size_t)hdr[2] * 8, ncclChar, root, comm, st));
+      }
+      et_data_build_csr(ctx, S);
+    } catch (...) {
+      et_data_free(S);
+      throw;
+    }
+    return S;
+  }
   et_data *D = (ctx->rank == root) ? data : et_data_alloc_internal(ctx, hdr[0], (int32_t)hdr[1]);
   try {
     const size_t bytes = (size_t)D->ld * (size_t)D->d * sizeof(double);

@@ -90,6 +90,9 @@ struct et_data {
   int32_t *csc_row = nullptr;
   double *csc_val = nullptr;
   int64_t csc_nnz = 0;
+  // ... and the row-major index of the same entries (which features a row stores; the order inside a row is free)
+  int64_t *csr_ptr = nullptr;  // [n + 1]
+  int32_t *csr_col = nullptr;
   // attached targets / weights (resident)
   int32_t *y_cls = nullptr;
   int32_t num_classes = 0;
@@ -165,6 +168,7 @@ void et_predict_device_impl(et_ctx *ctx, et_forest *f, const double *x_dev, int6
 void et_h2d(et_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t st);
 void et_stager_free(HostStager *s);
 et_data *et_data_alloc_internal(et_ctx *ctx, int64_t n, int32_t d);
+void et_data_build_csr(et_ctx *ctx, et_data *D);  // row-major index of a sparse-resident (CSC) table
 void et_predict_host_impl(et_ctx *ctx, et_forest *f, const double *x, int64_t n, int32_t d, double *out, int sum_only,
                           int want_regression);
 // dist.cu: the multi-GPU front context (et_init_multi) behind the ordinary calls

@@ -372,6 +372,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
         s_taken[w] = m;
       }
       team_sync<TEAM>();
+      if (!CODED && p.csr_ptr) sparse_mark_constant<TEAM>(p, rr, n, s_const, s_taken, W, tid);
       int nc = 0;
       for (int w = 0; w < W; w++) nc += __popc(s_const[w]);
       nconst = nc - (W * 32 - p.d);
@@ -1481,6 +1482,14 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? LANE_SMALL_CTAS : 4) 
       for (int o = 16; o > 0; o >>= 1) nc += __shfl_xor_sync(FULL, nc, o);
       nconst = nc - (W * 32 - p.d);
       __syncwarp();
+      if (!CODED && p.csr_ptr) {  // sparse-resident table: features none of the node's rows stores are constant
+        sparse_mark_constant<32>(p, idx, n, s_const, s_taken, W, lane);
+        nc = 0;
+        for (int w = lane; w < W; w += 32) nc += __popc(s_const[w]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nc += __shfl_xor_sync(FULL, nc, o);
+        nconst = nc - (W * 32 - p.d);
+      }
     }
     // Small nodes of a byte-coded table (free-running): which features vary over the node's rows is read off the
     // rows themselves in the row-major copy (n x 784 contiguous bytes: OR of the XORs with the first row, four

@@ -136,6 +136,44 @@ __device__ __forceinline__ bool chunk_ref(const WState &w, int64_t g, ChunkRef &
   return true;
 }
 
+// ---- CSC tables kept sparse: a chunk walks the stored entries of a column that fall into its row range --------
+// (both the chunk's rows and a column's stored rows ascend, so the range is two binary searches and membership of
+// an entry's row in the chunk one more, in shared memory; the rows of the chunk a column does not store are implicit
+// zeros and enter min / max and the side histograms by COUNT -- 12 bytes per stored entry visited instead of one
+// search per (row, candidate))
+__device__ __forceinline__ int chunk_pos(const int32_t *s_rows, int cnt, int32_t r) {
+  int lo = 0, hi = cnt;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (s_rows[mid] < r)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return (lo < cnt && s_rows[lo] == r) ? lo : -1;
+}
+__device__ __forceinline__ void col_range(const P &p, int32_t f, int32_t rmin, int32_t rmax, int64_t &lo_out, int64_t &hi_out) {
+  const int64_t a = __ldg(p.csc_colptr + f), e = __ldg(p.csc_colptr + f + 1);
+  int64_t lo = a, hi = e;
+  while (lo < hi) {  // first entry with row >= rmin
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(p.csc_row + mid) < rmin)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  lo_out = lo;
+  hi = e;
+  while (lo < hi) {  // first entry with row > rmax
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(p.csc_row + mid) <= rmax)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  hi_out = lo;
+}
+
 // ---- plan ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_wide_plan(P p, WState w) {
   __shared__ int64_t s_warp[32];
@@ -475,6 +513,46 @@ __global__ void __launch_bounds__(WT) k_wide_pass1(P p, WState w) {
   } else {
     if (w.bulk) mbar_wait(&s_bar, 0);
     __syncthreads();
+    if (p.csc_row) {
+      // sparse table: one warp per candidate walks the column's entries inside the chunk's row range
+      const int32_t rmin = s_rows[0], rmax = s_rows[r.cnt - 1];
+      for (int c = wit; c < nb; c += WT / 32) {
+        const int32_t f = cd.feat[c];
+        if (f < 0) continue;
+        int64_t lo, hi;
+        col_range(p, f, rmin, rmax, lo, hi);
+        double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;  // pkg:35-36
+        int32_t members = 0;
+        bool nan = false;
+        for (int64_t t = lo + lane; t < hi; t += 32) {
+          if (chunk_pos(s_rows, r.cnt, __ldg(p.csc_row + t)) >= 0) {
+            const double v = __ldg(p.csc_val + t);
+            members++;
+            if (v < mn) mn = v;
+            if (v > mx) mx = v;
+            nan |= (v != v);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double omn = __shfl_xor_sync(0xffffffffu, mn, o), omx = __shfl_xor_sync(0xffffffffu, mx, o);
+          if (omn < mn) mn = omn;
+          if (omx > mx) mx = omx;
+          members += __shfl_xor_sync(0xffffffffu, members, o);
+        }
+        nan = __any_sync(0xffffffffu, nan);
+        if (members < r.cnt) {  // the other rows of the chunk are implicit zeros
+          if (0.0 < mn) mn = 0.0;
+          if (0.0 > mx) mx = 0.0;
+        }
+        if (lane == 0) {
+          atomicMin(&cd.mn[c], dkey(mn));
+          atomicMax(&cd.mx[c], dkey(mx));
+          if (nan) atomicOr(&cd.nanmask, 1u << c);
+        }
+      }
+      return;
+    }
     double *park = (w.park && nb <= w.park_stride) ? w.park + (int64_t)blockIdx.x * w.park_stride * w.chunk : nullptr;
     // groups of 4 candidates, four rows per thread and trip: 16 independent gathers in flight
     for (int g0 = 0; g0 < nb; g0 += 4) {
@@ -741,7 +819,59 @@ __global__ void __launch_bounds__(WT) k_wide_pass2(P p, WState w) {
   __syncthreads();
   const int nsweep = nd.nsweep;
   const double *park = (!CODED && w.park && nb <= w.park_stride) ? w.park + (int64_t)blockIdx.x * w.park_stride * w.chunk : nullptr;
-  if (TASK == TASK_CLS) {
+  if (TASK == TASK_CLS && !CODED && p.csc_row) {
+    // sparse table: class histogram of the chunk once, then per candidate the histograms of the STORED rows (left /
+    // NaN / all); the rows the column does not store are zeros and go left iff 0 < cut, by count
+    __shared__ int32_t s_hc[32];
+    __shared__ int32_t s_wh[WT / 32][3][32];
+    if (tid < 32) s_hc[tid] = 0;
+    __syncthreads();
+    {
+      int32_t acc = 0;  // lane k counts class k over this warp's rows
+      for (int32_t j0 = wit * 32; j0 < r.cnt; j0 += WT) {
+        const int32_t j = j0 + lane;
+        const int32_t cls = (j < r.cnt) ? (int32_t)s_lab8[j] : -1;
+        for (int k = 0; k < C; k++) {
+          const uint32_t m = __ballot_sync(0xffffffffu, cls == k);
+          if (lane == k) acc += __popc(m);
+        }
+      }
+      if (lane < C && acc) atomicAdd(&s_hc[lane], acc);
+    }
+    __syncthreads();
+    const int32_t rmin = s_rows[0], rmax = s_rows[r.cnt - 1];
+    int32_t *gh = w.hist + (int64_t)r.q * 64 * C;
+    for (int c = wit; c < nb; c += WT / 32) {
+      if (!((act >> c) & 1u)) continue;
+      s_wh[wit][0][lane] = 0;
+      s_wh[wit][1][lane] = 0;
+      s_wh[wit][2][lane] = 0;
+      __syncwarp();
+      const double cut = s_cut[c];
+      int64_t lo, hi;
+      col_range(p, s_feat[c], rmin, rmax, lo, hi);
+      for (int64_t t = lo + lane; t < hi; t += 32) {
+        const int pos = chunk_pos(s_rows, r.cnt, __ldg(p.csc_row + t));
+        if (pos >= 0) {
+          const double v = __ldg(p.csc_val + t);
+          const int cls = (int)s_lab8[pos];
+          atomicAdd(&s_wh[wit][2][cls], 1);
+          if (v != v)
+            atomicAdd(&s_wh[wit][1][cls], 1);
+          else if (v < cut)
+            atomicAdd(&s_wh[wit][0][cls], 1);
+        }
+      }
+      __syncwarp();
+      if (lane < C) {
+        const int32_t hl = s_wh[wit][0][lane] + ((0.0 < cut) ? s_hc[lane] - s_wh[wit][2][lane] : 0);
+        const int32_t hn = s_wh[wit][1][lane];
+        if (hl) atomicAdd(&gh[c * 2 * C + lane], hl);
+        if (hn) atomicAdd(&gh[c * 2 * C + C + lane], hn);
+      }
+      __syncwarp();
+    }
+  } else if (TASK == TASK_CLS) {
     auto lab = [&](int32_t j) -> int32_t { return (int32_t)s_lab8[j]; };
     for (int sweep = 0; sweep < nsweep; sweep++) {
       const int hoff = sweep ? C : 0;
@@ -1132,6 +1262,45 @@ __global__ void __launch_bounds__(WT) k_wide_count(P p, WState w) {
   const Col col = CODED ? Col{nullptr, nullptr, 0} : col_of(p, bf);
   uint32_t *bits = w.bits + (int64_t)blockIdx.x * (w.chunk / 32);
   int32_t cntl = 0;
+  if (!CODED && p.csc_row) {
+    // sparse table: every row starts on the side of an implicit zero, the column's stored entries flip their rows
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_w[WCHUNK_MAX / 32];
+    int32_t *s_rows = reinterpret_cast<int32_t *>(smem_raw);
+    for (int32_t j = tid; j < r.cnt; j += WT) s_rows[j] = rr[j];
+    const bool zero_left = (0.0 < cut);
+    const int nwords = (r.cnt + 31) >> 5;
+    for (int t = tid; t < nwords; t += WT) {
+      const int rem = r.cnt - t * 32;
+      s_w[t] = zero_left ? (rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u)) : 0u;
+    }
+    __syncthreads();
+    int64_t lo, hi;
+    col_range(p, bf, s_rows[0], s_rows[r.cnt - 1], lo, hi);
+    for (int64_t t = lo + tid; t < hi; t += WT) {
+      const int pos = chunk_pos(s_rows, r.cnt, __ldg(p.csc_row + t));
+      if (pos >= 0) {
+        const double x = __ldg(p.csc_val + t);
+        const bool left = (x < cut) || (mil && (x != x));
+        if (left != zero_left) atomicXor(&s_w[pos >> 5], 1u << (pos & 31));  // (a row is stored at most once per column)
+      }
+    }
+    __syncthreads();
+    for (int t = tid; t < nwords; t += WT) {
+      bits[t] = s_w[t];
+      cntl += __popc(s_w[t]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cntl += __shfl_xor_sync(0xffffffffu, cntl, o);
+    if (lane == 0) s_cnt[wit] = cntl;
+    __syncthreads();
+    if (tid == 0) {
+      int32_t t = 0;
+      for (int w2 = 0; w2 < WT / 32; w2++) t += s_cnt[w2];
+      w.cnt_left[blockIdx.x] = t;
+    }
+    return;
+  }
   for (int32_t j0 = wit * 32; j0 < r.cnt; j0 += WT) {
     const int32_t j = j0 + lane;
     bool left = false;
@@ -1276,7 +1445,7 @@ void wide_level(et_ctx *ctx, const P &p, int32_t count, int64_t wide_rows, const
   wb.pending.ensure(2);
   // parked values of pass 1 (FP64 tables): [chunks][stride candidates][chunk rows]; kept within a third of the free HBM
   int park_stride = 0;
-  if (!coded) {
+  if (!coded && !p.csc_row) {
     static const bool no_park = getenv("ETGPU_NO_PARK") != nullptr && atoi(getenv("ETGPU_NO_PARK")) != 0;
     park_stride = no_park ? 0 : std::min(32, ((p.k + std::max(2, p.k / 4)) + 3) / 4 * 4);
     const size_t need = (size_t)max_chunks * (size_t)park_stride * (size_t)chunk;
@@ -1356,7 +1525,7 @@ void wide_level(et_ctx *ctx, const P &p, int32_t count, int64_t wide_rows, const
   if (coded)
     k_wide_count<true><<<gchunks, WT, 0, st>>>(p, w);
   else
-    k_wide_count<false><<<gchunks, WT, 0, st>>>(p, w);
+    k_wide_count<false><<<gchunks, WT, p.csc_row ? smem1 : 0, st>>>(p, w);
   k_wide_scatter<TASK><<<gchunks, WT, 0, st>>>(p, w);
   ctx->launches += 3;
   CUDA_CHECK(cudaGetLastError());

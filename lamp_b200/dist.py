@@ -5,8 +5,8 @@ pkg:653-675).  (One process driving several GPUs needs none of this: `Context.mu
 Trees are independent (per-tree random stream, pkg:654-655), so the build has NO data-path collective: rank r
 builds trees r, r+G, r+2G, ... (round-robin balances the depth lottery) from its own replica of the table.
 NCCL runs INSIDE libetgpu.so (dist.cu), on device buffers, only where the path has a real exchange:
-  * gather_forest  -> et_forest_allgather: ncclAllGather of the sizes, grouped ncclBroadcast of the packed 16-byte
-    nodes and leaf tables, trees put back in tree-id order by a kernel; every rank holds the whole forest;
+  * gather_forest  -> et_forest_allgather: ncclAllGather of the sizes, then of the packed 16-byte
+    nodes and leaf tables (slots padded to the largest shard), trees put back in tree-id order by a kernel; every rank holds the whole forest;
   * predict_*Sharded -> et_predict_*_allreduce: every rank traverses all rows for ITS trees, the per-row partial sums
     are ncclAllReduce'd in row chunks overlapped with the traversal, one division by the total tree count.  The
     reference sums leaf values in tree order (pkg:549,584); the sharded sum re-associates, so outputs agree to
