@@ -588,8 +588,34 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       out->leaf_bytes = std::max<size_t>(1, (size_t)segs[0].n_leaves * lw) * sizeof(double);
       segs.clear();
     } else {
-      CUDA_CHECK(cudaMalloc((void **)&out->d_nodes, std::max<size_t>(1, (size_t)node_base) * sizeof(PNode)));
-      CUDA_CHECK(cudaMalloc((void **)&out->d_leaf, std::max<size_t>(1, (size_t)leaf_base * lw) * sizeof(double)));
+      // (the batches' segments and the whole forest are alive together for a moment: when HBM is short -- 250 trees
+      // of a 10M-row table are 33 GB -- the per-batch workspace is given back first; the next build grows it again)
+      auto alloc_forest = [&](void **ptr, size_t bytes) {
+        if (cudaMalloc(ptr, bytes) == cudaSuccess) return;
+        cudaGetLastError();
+        for (int q = 0; q < 2; q++) {
+          ws.idx[q].release();
+          ws.yc[q].release();
+          ws.yr[q].release();
+          ws.ws[q].release();
+        }
+        ws.pool.tree.release();
+        ws.pool.feat.release();
+        ws.pool.child.release();
+        ws.pool.cut.release();
+        ws.pool.leaf_vals.release();
+        ws.size.release();
+        ws.nleaf.release();
+        ws.pos.release();
+        ws.lpos.release();
+        ws.scratch.release();
+        for (auto &b : ctx->cache) cudaFree(b.p);
+        ctx->cache.clear();
+        ctx->cache_bytes = 0;
+        CUDA_CHECK(cudaMalloc(ptr, bytes));
+      };
+      alloc_forest((void **)&out->d_nodes, std::max<size_t>(1, (size_t)node_base) * sizeof(PNode));
+      alloc_forest((void **)&out->d_leaf, std::max<size_t>(1, (size_t)leaf_base * lw) * sizeof(double));
       int64_t no = 0, lo = 0;
       for (auto &sg : segs) {
         CUDA_CHECK(cudaMemcpyAsync(out->d_nodes + no, sg.nodes, (size_t)sg.n_nodes * sizeof(PNode),

@@ -50,6 +50,9 @@ __host__ __device__ constexpr int stage_cap(int team) { return team == 32 ? 0 : 
 #ifndef CBIG_CTAS
 #define CBIG_CTAS 2
 #endif
+#ifndef MID_CODED_CTAS
+#define MID_CODED_CTAS 4  // resident 128-thread CTAs per SM of the byte-coded team for 513..2048-row nodes
+#endif
 constexpr int CBIG_TEAM = 256;    // threads of the CTA that owns a larger node of a byte-coded table
 constexpr int WARPS_PER_CTA = 4;  // warp teams per CTA in the small-node kernel
 

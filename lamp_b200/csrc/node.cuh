@@ -175,7 +175,7 @@ __device__ __forceinline__ void coded_pass2(const uint8_t *__restrict__ C8, cons
 template <int TASK, int TEAM, bool CODED>
 __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
                                   TEAM == 32 ? 5
-                                             : (TEAM == MID_TEAM ? (CODED ? 4 : 6)
+                                             : (TEAM == MID_TEAM ? (CODED ? MID_CODED_CTAS : 6)
                                                                  : ((TASK == TASK_REG && TEAM == CTA_TEAM) ? 1 : ((CODED && TEAM == CBIG_TEAM) ? CBIG_CTAS : 2))))
     k_node(P p, int32_t qcount, int qi) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

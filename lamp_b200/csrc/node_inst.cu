@@ -14,7 +14,10 @@ namespace {
 template <int TASK, typename VT>
 void launch_lane(et_ctx *ctx, const P &p, int32_t count, int qi, int NW, size_t smem_per_warp, cudaStream_t st) {
   const unsigned grid = (unsigned)ceil_div(count, LANE_WARPS);
-  if (NW <= 2)
+  // classes of up to 32 * small_nw rows run the register-lean variant (64 registers, 8 CTAs per SM); larger ones the
+  // variant that keeps 32 gathers of a lane in flight (128 registers, 4 CTAs per SM).  ETGPU_LANE_SMALL_NW moves it.
+  static const int small_nw = getenv("ETGPU_LANE_SMALL_NW") ? std::max(1, atoi(getenv("ETGPU_LANE_SMALL_NW"))) : 2;
+  if (NW <= small_nw)
     k_lane<TASK, VT, true><<<grid, 32 * LANE_WARPS, smem_per_warp * LANE_WARPS, st>>>(p, count, qi, NW);
   else
     k_lane<TASK, VT, false><<<grid, 32 * LANE_WARPS, smem_per_warp * LANE_WARPS, st>>>(p, count, qi, NW);
@@ -131,9 +134,9 @@ void set_smem_attr<ET_TASK>(const LevelCfg &lc) {
   }
   if (lc.coded) {
     CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(std::max(lc.smem_lane[0], lc.smem_lane[1]) * LANE_WARPS)));
+                                    (int)(lc.smem_lane[4] * LANE_WARPS)));
     CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(std::max(lc.smem_lane[2], std::max(lc.smem_lane[3], lc.smem_lane[4])) * LANE_WARPS)));
+                                    (int)(lc.smem_lane[4] * LANE_WARPS)));
   } else {
     CUDA_CHECK(cudaFuncSetAttribute(k_lane<TASK, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(lc.smem_lane[0] * LANE_WARPS)));

@@ -97,3 +97,28 @@ def test_comm_rank_collectives_on_a_group_of_one(mnist):
     assert np.array_equal(out.cpu().numpy(), et.predictClassification(shard, x, ctx=ctx))
     assert ctx.comm_last_ms() >= 0.0
     ctx.close()
+
+
+def test_multi_sparse_resident_table(group, monkeypatch):
+    """A CSC table that stays sparse in HBM replicates over the group (the three CSC arrays travel, the row-major index
+    is rebuilt per GPU) and builds the forest a single GPU builds."""
+    monkeypatch.setenv("ETGPU_CSC_DENSE_MAX", "0")
+    rng = np.random.default_rng(12)
+    n, d = 6000, 120
+    dense = np.where(rng.random((n, d)) < 0.03, np.abs(rng.normal(size=(n, d))) + 0.1, 0.0)
+    y = (dense[:, :20].sum(axis=1) > np.median(dense[:, :20].sum(axis=1))).astype(np.int32)
+    colptr = np.concatenate([[0], np.cumsum((dense != 0).sum(axis=0))]).astype(np.int64)
+    rowidx = np.concatenate([np.flatnonzero(dense[:, c]) for c in range(d)]).astype(np.int32)
+    vals = np.concatenate([dense[dense[:, c] != 0, c] for c in range(d)])
+    one = et.DeviceData.from_csc(colptr, rowidx, vals, n, d)
+    one.set_target_classification(y, 2)
+    many = et.DeviceData.from_csc(colptr, rowidx, vals, n, d, group)
+    many.set_target_classification(y, 2)
+    f1 = et.buildForestClassification(one, None, None, 2, 2, 10, 5, 4, seed=2)
+    f2 = et.buildForestClassification(many, None, None, 2, 2, 10, 5, 4, seed=2, ctx=group)
+    for t in range(5):
+        a, b = f1.flat(t), f2.flat(t)
+        assert np.array_equal(a.feature, b.feature) and np.array_equal(a.cut.view(np.int64), b.cut.view(np.int64))
+        assert np.array_equal(a.leaf, b.leaf)
+    one.free()
+    many.free()
