@@ -72,7 +72,7 @@ void *et_dev_alloc(et_ctx *ctx, size_t bytes) {
 void et_dev_free(et_ctx *ctx, void *p, size_t bytes) {
   if (!p) return;
   bytes = block_class(bytes);
-  const size_t kMaxBlocks = 16, kMaxBytes = (size_t)8 << 30;
+  const size_t kMaxBlocks = 32, kMaxBytes = (size_t)8 << 30;
   if (!ctx || bytes > kMaxBytes) {
     cudaFree(p);
     return;
@@ -1035,9 +1035,10 @@ et_forest::~et_forest() {
     return;
   }
   if (ctx) cudaSetDevice(ctx->device);
-  if (d_tree_off) cudaFree(d_tree_off);
+  if (d_tree_off && !tree_off_bytes) cudaFree(d_tree_off);
   std::unique_lock<std::recursive_mutex> lk;
   if (ctx) lk = std::unique_lock<std::recursive_mutex>(ctx->mu);
+  if (tree_off_bytes) et_dev_free(ctx, d_tree_off, tree_off_bytes);
   if (nodes_bytes)
     et_dev_free(ctx, d_nodes, nodes_bytes);
   else if (d_nodes)

@@ -131,22 +131,22 @@ __global__ void k_scatter(Pool o, int32_t n_nodes, int lw, const int32_t *pos, c
 
 // temporaries of one build call: freed on every exit path
 struct BuildTmp {
-  std::vector<void *> dev;
+  et_ctx *ctx = nullptr;
+  std::vector<std::pair<void *, size_t>> dev;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   BestBufs *best = nullptr;
+  // (blocks come from the context's cache: a small build is not a string of cudaMalloc / cudaFree pairs)
   template <typename T>
   T *upload(const T *h, size_t n, cudaStream_t st) {
-    T *d = nullptr;
-    if (cudaMalloc((void **)&d, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) {
-      cudaGetLastError();
-      ET_FAIL(ET_ENOMEM, "device allocation failed");
-    }
-    dev.push_back(d);
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    T *d = static_cast<T *>(et_dev_alloc(ctx, bytes));
+    if (!d) ET_FAIL(ET_ENOMEM, "device allocation failed");
+    dev.push_back({d, bytes});
     if (n) CUDA_CHECK(cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, st));
     return d;
   }
   ~BuildTmp() {
-    for (void *d : dev) cudaFree(d);
+    for (auto &d : dev) et_dev_free(ctx, d.first, d.second);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (best) best_bufs_destroy(best);
@@ -201,6 +201,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
   EventTimer evt;
   double tacc[2] = {0, 0};
   BuildTmp tmp;
+  tmp.ctx = ctx;
 
   // candidates per batch: bounded by 32 lanes and by the team's shared memory
   int NB = 32;
@@ -394,8 +395,6 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       p.r8_stride = (int32_t)D->rs8;
       p.nc_max = 64;
       if (const char *env = getenv("ETGPU_NC_MAX")) p.nc_max = std::max(0, atoi(env));
-      p.XR = D->xr;
-      p.xr_stride = (int32_t)D->rsd;
       p.lane_nb = lane_nb;
       p.csc_colptr = D->csc_colptr;
       p.csc_row = D->csc_row;
@@ -629,7 +628,9 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       for (auto &sg : segs) free_seg(sg);
       segs.clear();
     }
-    CUDA_CHECK(cudaMalloc((void **)&out->d_tree_off, ((size_t)a.m + 1) * sizeof(int64_t)));
+    out->tree_off_bytes = ((size_t)a.m + 1) * sizeof(int64_t);
+    out->d_tree_off = static_cast<int64_t *>(et_dev_alloc(ctx, out->tree_off_bytes));
+    if (!out->d_tree_off) ET_FAIL(ET_ENOMEM, "device allocation failed");
     CUDA_CHECK(cudaMemcpyAsync(out->d_tree_off, out->tree_off.data(), ((size_t)a.m + 1) * sizeof(int64_t),
                                cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaEventRecord(tmp.ev1, st));

@@ -197,8 +197,6 @@ struct P {
   const uint8_t *R8;   // row-major byte codes [n][r8_stride] (gathered by k_lane)
   int32_t r8_stride;
   int32_t nc_max;      // k_lane: nodes of up to this many rows draw from their varying-feature set
-  const double *XR;    // row-major FP64 [n][xr_stride]
-  int32_t xr_stride;
   int32_t lane_nb;     // k_lane on FP64 tables: candidates per batch (parked values per row), <= 32
   // CSC table (X == null): column f holds the entries csc_colptr[f] .. csc_colptr[f + 1] - 1 of (csc_row, csc_val)
   const int64_t *csc_colptr;

@@ -177,48 +177,30 @@ __global__ void __launch_bounds__(256) k_to_rowmajor(const T *__restrict__ src, 
 
 void et_data_drop_rowmajor(et_data *D) {
   et_dev_free(D->ctx, D->r8, D->r8_bytes);
-  et_dev_free(D->ctx, D->xr, D->xr_bytes);
   D->r8 = nullptr;
-  D->xr = nullptr;
-  D->r8_bytes = D->xr_bytes = 0;
+  D->r8_bytes = 0;
 }
 
-// Builds the row-major copy k_lane gathers from (byte codes if the table is coded; the FP64 one only on request,
-// ETGPU_ROWMAJOR_FP64=1).  A failed allocation just leaves the copy absent: the kernels then gather by column.
+// Builds the row-major copy of the byte codes k_lane gathers from.  A failed allocation just leaves the copy
+// absent: the kernels then gather by column.  (A row-major FP64 copy was tried and dropped: with k << d the k values
+// of a row sit in as many 32-byte sectors as k column gathers do.)
 void et_data_rowmajor(et_ctx *ctx, et_data *D) {
-  if (D->n <= 0 || D->d <= 0 || D->coded == 0) return;
-  const char *env = getenv("ETGPU_ROWMAJOR_FP64");
-  const bool fp64_on = env && atoi(env) > 0;
-  if (D->coded != 1 && !fp64_on) return;
+  if (D->n <= 0 || D->d <= 0 || D->coded != 1 || D->r8) return;
   if (const char *e2 = getenv("ETGPU_NO_ROWMAJOR"))
     if (atoi(e2) != 0) return;
   cudaStream_t st = ctx->stream;
   dim3 block(32, 8), grid((unsigned)ceil_div(D->n, 32), (unsigned)ceil_div(D->d, 32));
-  if (D->coded == 1 && !D->r8) {
-    D->rs8 = ((int64_t)D->d + 15) / 16 * 16;
-    D->r8_bytes = (size_t)D->n * (size_t)D->rs8;
-    D->r8 = static_cast<uint8_t *>(et_dev_alloc(ctx, D->r8_bytes));
-    if (!D->r8) {
-      D->r8_bytes = 0;
-      cudaGetLastError();
-      return;
-    }
-    cudaMemsetAsync(D->r8, 0, D->r8_bytes, st);
-    k_to_rowmajor<uint8_t><<<grid, block, 0, st>>>(D->c8, D->ldc, D->n, D->d, D->r8, D->rs8);
-    ctx->launches++;
-  } else if (D->coded == -1 && !D->xr) {
-    D->rsd = ((int64_t)D->d + 1) / 2 * 2;
-    D->xr_bytes = (size_t)D->n * (size_t)D->rsd * sizeof(double);
-    D->xr = static_cast<double *>(et_dev_alloc(ctx, D->xr_bytes));
-    if (!D->xr) {
-      D->xr_bytes = 0;
-      cudaGetLastError();
-      return;
-    }
-    cudaMemsetAsync(D->xr, 0, D->xr_bytes, st);
-    k_to_rowmajor<double><<<grid, block, 0, st>>>(D->x, D->ld, D->n, D->d, D->xr, D->rsd);
-    ctx->launches++;
+  D->rs8 = ((int64_t)D->d + 15) / 16 * 16;
+  D->r8_bytes = (size_t)D->n * (size_t)D->rs8;
+  D->r8 = static_cast<uint8_t *>(et_dev_alloc(ctx, D->r8_bytes));
+  if (!D->r8) {
+    D->r8_bytes = 0;
+    cudaGetLastError();
+    return;
   }
+  cudaMemsetAsync(D->r8, 0, D->r8_bytes, st);
+  k_to_rowmajor<uint8_t><<<grid, block, 0, st>>>(D->c8, D->ldc, D->n, D->d, D->r8, D->rs8);
+  ctx->launches++;
 }
 
 void et_data_drop_codes(et_data *D) {

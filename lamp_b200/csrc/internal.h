@@ -78,13 +78,11 @@ struct et_data {
   uint8_t *coff = nullptr; // [d] 0 if the column holds a NaN, else 1
   int64_t ldc = 0;         // code column stride in bytes (n rounded up to 128)
   double *dict = nullptr;  // [d][256] ascending distinct values, padded with +inf
-  // row-major copies gathered by the lane-per-candidate kernel (k_lane): byte codes [n][rs8] when the table is
-  // coded, else FP64 [n][rsd]; rows are 16-byte multiples so a row moves with full vector loads
+  // row-major copy of the byte codes gathered by the lane-per-candidate kernel (k_lane): [n][rs8]; rows are 16-byte
+  // multiples so a row moves with full vector loads
   uint8_t *r8 = nullptr;
   int64_t rs8 = 0;   // bytes per coded row
-  double *xr = nullptr;
-  int64_t rsd = 0;   // doubles per FP64 row
-  size_t r8_bytes = 0, xr_bytes = 0;
+  size_t r8_bytes = 0;
   // CSC table kept sparse in HBM (x == null): ascending rows without duplicates inside every column
   int64_t *csc_colptr = nullptr;  // [d + 1]
   int32_t *csc_row = nullptr;
@@ -126,7 +124,7 @@ struct et_forest {
   int64_t *d_tree_off = nullptr;  // m + 1
   PNode *d_nodes = nullptr;       // total_nodes
   double *d_leaf = nullptr;       // total_leaves x leaf_width
-  size_t nodes_bytes = 0, leaf_bytes = 0;  // allocation sizes when the blocks came from et_dev_alloc (else 0)
+  size_t nodes_bytes = 0, leaf_bytes = 0, tree_off_bytes = 0;  // allocation sizes when the blocks came from et_dev_alloc (else 0)
   // multi-GPU: sort key of every tree when shards are gathered (global tree id / position in the call's forest)
   std::vector<int64_t> order_key;
   // multi-GPU front handle: the per-GPU forests of the trees each GPU built, and the gathered whole forest (on the

@@ -177,7 +177,11 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
                                   TEAM == 32 ? 5
                                              : (TEAM == MID_TEAM ? (CODED ? MID_CODED_CTAS : 6)
                                                                  : ((TASK == TASK_REG && TEAM == CTA_TEAM) ? 1 : ((CODED && TEAM == CBIG_TEAM) ? CBIG_CTAS : 2))))
-    k_node(P p, int32_t qcount, int qi) {
+    k_node(P p, int32_t qcount, int qi, int lane_mode = 0) {
+  // lane_mode: the queue is one of k_lane's size classes, handed to CTA teams because the level holds too few such
+  // nodes to fill the GPU with single warps (launch_level): the node histogram is not in the frontier (k_lane
+  // parents do not write it) and the batch sizes follow k_lane's rule, so that the draws -- and the tree -- do not
+  // depend on which kernel ran.
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool WARP = (TEAM == 32);
   static_assert(!CODED || (TASK == TASK_CLS && TEAM > 32), "byte-coded teams: unweighted classification, CTA teams");
@@ -256,7 +260,13 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
   double reg_mu = 0.0, reg_S = 0.0, reg_Q = 0.0;  // REGPAR: node mean, sum and sum of squares of (y - mean)
   double second_score = -INFINITY;                // REGPAR: runner-up score (ambiguity check)
   if (TASK == TASK_CLS) {
-    for (int c = tid; c < C; c += TEAM) s_hnode[c] = p.cur.hist[(int64_t)i * C + c];
+    if (lane_mode) {
+      for (int c = tid; c < C; c += TEAM) s_hnode[c] = 0;
+      team_sync<TEAM>();
+      for (int32_t j = tid; j < n; j += TEAM) atomicAdd(&s_hnode[LAB(j)], 1);
+    } else {
+      for (int c = tid; c < C; c += TEAM) s_hnode[c] = p.cur.hist[(int64_t)i * C + c];
+    }
     team_sync<TEAM>();
     bool pure = false;
     for (int c = 0; c < C; c++) pure |= (s_hnode[c] == n);
@@ -411,8 +421,16 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
         // which stops drawing there
         const int32_t need = min(p.k - visited, avail);
         int32_t extra = 0;
-        if (need > 0 && st_draws > 0)
+        if (lane_mode) {  // k_lane's rule, verbatim
+          if (st_draws > 0)
+            extra = (st_draws > (unsigned long long)visited)
+                        ? (int32_t)(((long long)need * (long long)(st_draws - (unsigned long long)visited)) / max(visited, 1)) + 2
+                        : 0;
+          else
+            extra = (nconst > 0) ? need + 4 : 0;
+        } else if (need > 0 && st_draws > 0) {
           extra = (int32_t)(((long long)need * (long long)(st_draws - (unsigned long long)visited)) / max(visited, 1));
+        }
         nb = min(NB, min(avail, need + extra));
         if (need <= 0) nb = 0;
       }

@@ -11,12 +11,17 @@ namespace etb {
 
 namespace {
 
+int lane_small_nw() {
+  static const int v = getenv("ETGPU_LANE_SMALL_NW") ? std::max(1, atoi(getenv("ETGPU_LANE_SMALL_NW"))) : 2;
+  return v;
+}
+
 template <int TASK, typename VT>
 void launch_lane(et_ctx *ctx, const P &p, int32_t count, int qi, int NW, size_t smem_per_warp, cudaStream_t st) {
   const unsigned grid = (unsigned)ceil_div(count, LANE_WARPS);
+  const int small_nw = lane_small_nw();
   // classes of up to 32 * small_nw rows run the register-lean variant (64 registers, 8 CTAs per SM); larger ones the
   // variant that keeps 32 gathers of a lane in flight (128 registers, 4 CTAs per SM).  ETGPU_LANE_SMALL_NW moves it.
-  static const int small_nw = getenv("ETGPU_LANE_SMALL_NW") ? std::max(1, atoi(getenv("ETGPU_LANE_SMALL_NW"))) : 2;
   if (NW <= small_nw)
     k_lane<TASK, VT, true><<<grid, 32 * LANE_WARPS, smem_per_warp * LANE_WARPS, st>>>(p, count, qi, NW);
   else
@@ -26,8 +31,9 @@ void launch_lane(et_ctx *ctx, const P &p, int32_t count, int qi, int NW, size_t 
 
 // the byte-coded CTA teams exist for unweighted classification only
 template <int TASK, int TEAM>
-void launch_coded_team(const P &p, int32_t count, int qi, size_t smem, cudaStream_t st) {
-  if constexpr (TASK == TASK_CLS) k_node<TASK_CLS, TEAM, true><<<(unsigned)count, TEAM, smem, st>>>(p, count, qi);
+void launch_coded_team(const P &p, int32_t count, int qi, size_t smem, cudaStream_t st, int lane_mode = 0) {
+  if constexpr (TASK == TASK_CLS)
+    k_node<TASK_CLS, TEAM, true><<<(unsigned)count, TEAM, smem, st>>>(p, count, qi, lane_mode);
 }
 
 template <int TASK>
@@ -90,14 +96,32 @@ void launch_level<ET_TASK>(et_ctx *ctx, const P &p, const int32_t *qn, int64_t w
     ctx->launches++;
     pt.stop(PhaseTimer::MID);
   }
+  // A warp walks its node's rows one after the other: a level that holds only a few nodes of a large lane class
+  // lasts as long as that chain (0.3 ms for 512 rows) while the GPU idles -- the tail levels of every build, and
+  // most levels when the forest is sharded over 8 GPUs.  Such a class goes to the 128-thread CTA teams instead
+  // (a quarter of the chain; same draws and same tree, see k_node's lane_mode).  ETGPU_TEAM_MAX moves the bound
+  // (nodes per class and level; 0 = never).
+  static const int small_nw = lane_small_nw();
+  int team_max = 2 * 148;
+  if (const char *env = getenv("ETGPU_TEAM_MAX")) team_max = std::max(0, atoi(env));
   for (int q = Q_WARP; q >= 0; q--) {
     if (qn[q] <= 0) continue;
     pt.start();
     cudaStream_t st = stream_for(q);
-    if (lc.coded) {
+    const bool to_team = q >= 2 && (1 << q) > small_nw && qn[q] <= team_max && p.NB == 32;
+    if (lc.coded && to_team) {
+      if (lc.coded_big)
+        launch_coded_team<TASK, MID_TEAM>(p, qn[q], q, lc.smem_mid, st, 1);
+      else
+        k_node<TASK, MID_TEAM, false><<<(unsigned)qn[q], MID_TEAM, lc.smem_mid, st>>>(p, qn[q], q, 1);
+      ctx->launches++;
+    } else if (lc.coded) {
       launch_lane<TASK, uint8_t>(ctx, p, qn[q], q, 1 << q, lc.smem_lane[q], st);
     } else if (q == Q_LANE0) {
       launch_lane<TASK, double>(ctx, p, qn[q], q, 1, lc.smem_lane[0], st);
+    } else if (qn[q] <= team_max && p.NB == 32) {  // FP64 tables, few nodes: CTA teams (same kernel, wider team)
+      k_node<TASK, MID_TEAM, false><<<(unsigned)qn[q], MID_TEAM, lc.smem_mid, st>>>(p, qn[q], q, 0);
+      ctx->launches++;
     } else {  // FP64 tables: only class Q_WARP is populated besides class Q_LANE0
       k_node<TASK, 32, false>
           <<<(unsigned)ceil_div(qn[q], WARPS_PER_CTA), 32 * WARPS_PER_CTA, lc.smem_warp * WARPS_PER_CTA, st>>>(p, qn[q], q);

@@ -526,6 +526,48 @@ def test_wide_and_one_cta_paths_build_the_same_free_running_forest(mnist, monkey
         assert a.stats[key] == b.stats[key], key
 
 
+def _same_forest(a, b, m):
+    for t in range(m):
+        fa, fb = a.flat(t), b.flat(t)
+        assert np.array_equal(fa.feature, fb.feature) and np.array_equal(fa.cut.view(np.int64), fb.cut.view(np.int64))
+        assert np.array_equal(fa.leaf.view(np.int64), fb.leaf.view(np.int64))
+    for key in ("v_mm", "v_sc", "s_rows", "p_rows", "draws", "const_hits", "scored", "nodes"):
+        assert a.stats[key] == b.stats[key], key
+
+
+def test_lane_classes_on_cta_teams_build_the_same_forest(mnist, monkeypatch):
+    """A level with few nodes of a lane class (129..512 rows) hands them to 128-thread CTA teams (launch_level,
+    ETGPU_TEAM_MAX): same draws, same scores, same tree -- free-running forests must not depend on how many nodes a
+    level happens to hold (shard independence), and replay stays bit-exact on the team path."""
+    x, y = mnist
+    x, y = x[:6000], y[:6000]
+    w = 0.25 + (np.arange(6000) % 7) / 4.0
+    xr, yr = synth_regression(6000, 10, 4, nan_frac=0.05)
+    xs, ys = synth_classification(5000, 12, 3, 5, nan_frac=0.1, const_cols=2, quantize=2)
+    built = {}
+    for team_max in ("0", "1000000000"):
+        monkeypatch.setenv("ETGPU_TEAM_MAX", team_max)
+        built[team_max] = (
+            et.buildForestClassification(x, y, None, 10, 2, 28, 3, 4, seed=31),
+            et.buildForestClassification(x, y, w, 10, 2, 28, 2, 4, seed=32),
+            et.buildForestRegression(xr, yr, 5, 3, 3, 4, seed=33),
+            et.buildForestClassification(xs, ys, None, 3, 2, 4, 3, 2, seed=34),
+        )
+    for (a, b, m) in zip(built["0"], built["1000000000"], (3, 2, 3, 3)):
+        _same_forest(a, b, m)
+    monkeypatch.setenv("ETGPU_TEAM_MAX", "1000000000")
+    of = O.build_forest_classification(x, y, None, 10, 2, 28, 2, 2, seed=17, record_trace=True)
+    gf = et.buildForestClassification(x, y, None, 10, 2, 28, 2, 2, seed=17, replay=oracle_replay(of))
+    assert_trees_bit_exact(gf, of)
+    assert gf.stats["replay_mismatches"] == 0
+    of = O.build_forest_classification(x, y, w, 10, 2, 28, 1, 1, seed=18, record_trace=True)
+    gf = et.buildForestClassification(x, y, w, 10, 2, 28, 1, 1, seed=18, replay=oracle_replay(of))
+    assert_trees_bit_exact(gf, of)
+    of = O.build_forest_regression(xr, yr, 5, 3, 2, 2, seed=3, record_trace=True)
+    gf = et.buildForestRegression(xr, yr, 5, 3, 2, 2, seed=3, replay=oracle_replay(of))
+    assert_trees_bit_exact(gf, of)
+
+
 # ---- argument handling (advisor findings, round 1) ---------------------------------------------------------------
 def test_predict_rejects_samples_narrower_than_the_split_features(mnist):
     x, y = mnist
