@@ -443,8 +443,11 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
         ws.fr[cn].ensure((size_t)F * 2, C, W, task == TASK_CLS, !replay);
         for (int q = 0; q < NQ; q++) ws.q[cn][q].ensure((size_t)F * 2, 1.5);
         ws.pool.grow((size_t)(n_nodes + 2 * (int64_t)F), (size_t)n_nodes, (size_t)leaf_bound, (size_t)n_leaves, lw, st);
-        if (task != TASK_CLS && qn[Q_MID] + qn[Q_CTA] > 0)
-          ws.scratch.ensure((size_t)NB * 2 * ((size_t)Bt * (size_t)n / 32 + (size_t)(qn[Q_MID] + qn[Q_CTA]) + 1) + 64, 1.0);
+        {  // side-bit scratch of the CTA teams (weighted / regression); lane classes may be handed to teams (launch_level)
+          const size_t teams = (size_t)qn[2] + (size_t)qn[3] + (size_t)qn[Q_WARP] + (size_t)qn[Q_MID] + (size_t)qn[Q_CTA];
+          if (task != TASK_CLS && teams > 0)
+            ws.scratch.ensure((size_t)NB * 2 * ((size_t)Bt * (size_t)n / 32 + teams + 1) + 64, 1.0);
+        }
         pt.stop(PhaseTimer::ALLOC);
         p.idx_src = ws.idx[srcb].p;
         p.idx_dst = ws.idx[srcb ^ 1].p;

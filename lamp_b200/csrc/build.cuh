@@ -242,6 +242,38 @@ __device__ __forceinline__ double col_at(const Col &c, int32_t r) {
   return (lo < c.nnz && __ldg(c.rows + lo) == r) ? __ldg(c.v + lo) : 0.0;
 }
 
+// U rows of one column at once.  On a CSC column the U searches advance in lockstep (the halving steps depend only
+// on the column's length), so their loads overlap: a one-team kernel's time on a sparse table is the chain of
+// dependent row-id loads, and this cuts it by U.  r[u] < 0 = no row (x[u] = 0.0).
+template <int U>
+__device__ __forceinline__ void col_atn(const Col &c, const int32_t (&r)[U], double (&x)[U]) {
+  if (!c.rows) {
+#pragma unroll
+    for (int u = 0; u < U; u++) x[u] = (r[u] >= 0) ? __ldg(c.v + r[u]) : 0.0;
+    return;
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++) x[u] = 0.0;
+  if (c.nnz <= 0) return;
+  int32_t b[U];  // offsets into the column's stored rows
+#pragma unroll
+  for (int u = 0; u < U; u++) b[u] = 0;
+  int len = c.nnz;
+  while (len > 1) {  // first entry with row >= r[u] lies in [b[u], b[u] + len]
+    const int half = len >> 1;
+#pragma unroll
+    for (int u = 0; u < U; u++) b[u] = (__ldg(c.rows + b[u] + half - 1) < r[u]) ? b[u] + half : b[u];
+    len -= half;
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const int32_t v0 = __ldg(c.rows + b[u]);
+    const int32_t at = (v0 < r[u]) ? b[u] + 1 : b[u];
+    if (r[u] >= 0 && at < c.nnz && ((v0 == r[u]) || (v0 < r[u] && __ldg(c.rows + at) == r[u]))) x[u] = __ldg(c.v + at);
+  }
+}
+__device__ __forceinline__ void col_at4(const Col &c, const int32_t (&r)[4], double (&x)[4]) { col_atn<4>(c, r, x); }
+
 __host__ __device__ inline int size_class(const P &p, int64_t n) {
   int q = 0;
   while (q < NQ - 1 && n > p.cls_max[q]) q++;

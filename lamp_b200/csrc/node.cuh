@@ -771,39 +771,54 @@ __global__ void __launch_bounds__(TEAM == 32 ? 32 * WARPS_PER_CTA : TEAM,
         int has_nan = 0;
         if (WARP) {
           // one gather per sample: the values are parked in shared memory for the second pass
-#pragma unroll 4
-          for (int v = 0; v < nv; v++) {
-            const int j = v * 32 + lane;
-            if (j < n) {
-              const double x = col_at(col, s_rows[j]);
-              s_xs[j] = x;
-              if (x < mn) mn = x;
-              if (x > mx) mx = x;
-              has_nan |= (x != x);
-            }
-          }
-        } else {
-          for (int32_t j0 = 0; j0 < n; j0 += 4 * TEAM) {
+          for (int v0 = 0; v0 < nv; v0 += 4) {
             int32_t r4[4];
             double x4[4];
 #pragma unroll
             for (int u2 = 0; u2 < 4; u2++) {
-              const int32_t j = j0 + u2 * TEAM + tid;
-              r4[u2] = (j < n) ? rr[j] : -1;
+              const int j = (v0 + u2) * 32 + lane;
+              r4[u2] = (j < n) ? s_rows[j] : -1;
             }
-#pragma unroll
-            for (int u2 = 0; u2 < 4; u2++) x4[u2] = (r4[u2] >= 0) ? col_at(col, r4[u2]) : 0.0;
+            col_at4(col, r4, x4);
 #pragma unroll
             for (int u2 = 0; u2 < 4; u2++) {
               if (r4[u2] >= 0) {
                 const double x = x4[u2];
-                if (staged) s_xs[j0 + u2 * TEAM + tid] = x;
+                s_xs[(v0 + u2) * 32 + lane] = x;
                 if (x < mn) mn = x;
                 if (x > mx) mx = x;
                 has_nan |= (x != x);
               }
             }
           }
+        } else {
+          auto sweep = [&](auto uu) {  // U rows per thread and trip
+            constexpr int U = decltype(uu)::value;
+            for (int32_t j0 = 0; j0 < n; j0 += U * TEAM) {
+              int32_t r4[U];
+              double x4[U];
+#pragma unroll
+              for (int u2 = 0; u2 < U; u2++) {
+                const int32_t j = j0 + u2 * TEAM + tid;
+                r4[u2] = (j < n) ? rr[j] : -1;
+              }
+              col_atn<U>(col, r4, x4);
+#pragma unroll
+              for (int u2 = 0; u2 < U; u2++) {
+                if (r4[u2] >= 0) {
+                  const double x = x4[u2];
+                  if (staged) s_xs[j0 + u2 * TEAM + tid] = x;
+                  if (x < mn) mn = x;
+                  if (x > mx) mx = x;
+                  has_nan |= (x != x);
+                }
+              }
+            }
+          };
+          if (col.rows)
+            sweep(std::integral_constant<int, 8>{});  // sparse table: eight searches in lockstep
+          else
+            sweep(std::integral_constant<int, 4>{});
         }
         team_minmax<TEAM>(mn, mx, has_nan, s_redd, s_redi);
         if (mx <= mn && !has_nan) {  // pkg:236
@@ -1720,7 +1735,39 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, SMALL ? LANE_SMALL_CTAS : 4) 
           }
         }
       };
-      if (CODED && p.c8_small)
+      bool sparse_done = false;
+      if constexpr (!CODED) {
+       if (p.csc_row) {
+        // sparse table: four rows of the lane's column in lockstep (col_at4)
+        sparse_done = true;
+        for (int w = 0; w < nw; w++) {
+          const int j0 = w << 5, cnt = min(32, n - j0);
+          const int32_t row = (lane < cnt) ? idx[j0 + lane] : 0;
+          for (int jj = 0; jj < cnt; jj += 4) {
+            int32_t r4[4];
+            double x4[4];
+#pragma unroll
+            for (int u2 = 0; u2 < 4; u2++) {
+              const int32_t rj = __shfl_sync(FULL, row, (jj + u2) & 31);
+              r4[u2] = (act0 && jj + u2 < cnt) ? rj : -1;
+            }
+            col_at4(dcol, r4, x4);
+#pragma unroll
+            for (int u2 = 0; u2 < 4; u2++) {
+              if (jj + u2 < cnt) {
+                const double x = x4[u2];
+                if (lane < LNB) s_x[(j0 + jj + u2) * LNB + lane] = (VT)x;
+                if (x < mn) mn = x;
+                if (x > mx) mx = x;
+                has_nan |= (x != x);
+              }
+            }
+          }
+        }
+       }
+      }
+      if (sparse_done) {
+      } else if (CODED && p.c8_small)
         pass1(std::true_type{});
       else
         pass1(std::false_type{});

@@ -1,17 +1,18 @@
 #!/bin/bash
-# tuning sweep (rebuilds on the box): lane class variants and the residency of the coded 128-thread team
+# sparse full size: chunk size of the walk x bound above which a node takes the chunked path
 mkdir -p gpurun_out
-{
-for v in 2 4 8; do echo "== ETGPU_LANE_SMALL_NW=$v"; ETGPU_LANE_SMALL_NW=$v timeout 300 python scripts/one_build.py mnist 500 4 2>&1 | tail -3 | cut -c1-120; done
-for c in 5 6 3; do
-  touch lamp_b200/csrc/node_inst.cu
-  make -C lamp_b200/csrc -j16 -s EXTRA="-DMID_CODED_CTAS=$c" > /dev/null 2>&1
-  echo "== MID_CODED_CTAS=$c"; timeout 300 python scripts/one_build.py mnist 500 4 2>&1 | tail -3 | cut -c1-120
+S=gpurun_out/r2_sparse_chunk_sweep.txt
+: > $S
+for wm in 2048 512; do
+for ch in 256 512 1024 2048; do
+  echo "== 2 trees ETGPU_WIDE_CHUNK=$ch ETGPU_SPARSE_WIDE_MIN=$wm" >> $S
+  ETGPU_WIDE_CHUNK=$ch ETGPU_SPARSE_WIDE_MIN=$wm timeout 300 python scripts/sparse_full.py 2 2>&1 | grep "trees built" | cut -c1-200 >> $S
 done
-for c in 10; do
-  touch lamp_b200/csrc/node_inst.cu
-  make -C lamp_b200/csrc -j16 -s EXTRA="-DLANE_SMALL_CTAS=$c" > /dev/null 2>&1
-  echo "== LANE_SMALL_CTAS=$c"; timeout 300 python scripts/one_build.py mnist 500 4 2>&1 | tail -3 | cut -c1-120
 done
-} > gpurun_out/r2_tuning_sweep.log 2>&1
-cat gpurun_out/r2_tuning_sweep.log
+for wm in 2048 512; do
+  echo "== 16 trees ETGPU_WIDE_CHUNK=512 ETGPU_SPARSE_WIDE_MIN=$wm" >> $S
+  ETGPU_WIDE_CHUNK=512 ETGPU_SPARSE_WIDE_MIN=$wm timeout 300 python scripts/sparse_full.py 16 2>&1 | grep "trees built" | cut -c1-200 >> $S
+done
+cat $S
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "csc or sparse" > gpurun_out/r2_tests13.log 2>&1; echo "tests rc=$?" >> gpurun_out/r2_tests13.log
+tail -3 gpurun_out/r2_tests13.log | cut -c1-200

@@ -568,6 +568,30 @@ def test_lane_classes_on_cta_teams_build_the_same_forest(mnist, monkeypatch):
     assert_trees_bit_exact(gf, of)
 
 
+def test_small_regression_and_weighted_tables_in_a_fresh_context():
+    """Tables whose every node sits in a lane class (<= 512 rows), built first thing in a new context: the CTA teams
+    these classes are handed to keep their side bits in a scratch buffer that must be sized for them too (it used
+    to be sized for the 513+ row classes only, and was a null pointer here)."""
+    xr, yr = synth_regression(400, 6, 11, nan_frac=0.05)
+    xs, ys = synth_classification(450, 8, 3, 12, nan_frac=0.05)
+    w = 0.5 + (np.arange(450) % 5) / 3.0
+    ofr = O.build_forest_regression(xr, yr, 3, 3, 4, 2, seed=4, record_trace=True)
+    ofw = O.build_forest_classification(xs, ys, w, 3, 2, 3, 4, 2, seed=5, record_trace=True)
+    for first in ("reg", "clsw"):
+        ctx = et.Context(0)
+        try:
+            order = [("reg", ofr), ("clsw", ofw)] if first == "reg" else [("clsw", ofw), ("reg", ofr)]
+            for kind, of in order:
+                if kind == "reg":
+                    gf = et.buildForestRegression(xr, yr, 3, 3, 4, 2, seed=4, replay=oracle_replay(of), ctx=ctx)
+                else:
+                    gf = et.buildForestClassification(xs, ys, w, 3, 2, 3, 4, 2, seed=5, replay=oracle_replay(of), ctx=ctx)
+                assert_trees_bit_exact(gf, of)
+                del gf
+        finally:
+            ctx.close()
+
+
 # ---- argument handling (advisor findings, round 1) ---------------------------------------------------------------
 def test_predict_rejects_samples_narrower_than_the_split_features(mnist):
     x, y = mnist
