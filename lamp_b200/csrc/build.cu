@@ -401,6 +401,7 @@ void et_build_forest(et_ctx *ctx, et_data *D, const BuildArgs &a, et_forest *out
       p.csc_val = D->csc_val;
       p.csr_ptr = D->csr_ptr;
       p.csr_col = D->csr_col;
+      p.inv_rows = (int64_t)Bt * n;
       p.tr = trace;
       int srcb = 0, cl = 0;  // cl: frontier slot of the current level
       int32_t F = Bt;

@@ -205,6 +205,7 @@ struct P {
   // ... and its row-major index (which features a row stores): csr_col[csr_ptr[r] .. csr_ptr[r + 1])
   const int64_t *csr_ptr;
   const int32_t *csr_col;
+  int64_t inv_rows;  // trees of the batch x n (size of the chunked path's inverse index map)
 };
 
 // Column f of the table: dense FP64 values, or the stored entries of a CSC column (everything not stored is 0.0

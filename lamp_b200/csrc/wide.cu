@@ -81,6 +81,9 @@ struct WState {
   // nodes whose batch holds more than park_stride candidates gather twice.  null: off
   double *park;
   int32_t park_stride;
+  // sparse-resident tables: inv[tree * n + row] = position of the row inside the tree's index segment, written each
+  // level for the rows of the wide nodes (k_wide_inv); entries of other rows are stale and are validated on use
+  int32_t *inv;
 };
 
 // Stages `cnt` sample indices of a node's contiguous segment in shared memory (s_buf: 16-byte aligned, room for
@@ -141,6 +144,15 @@ __device__ __forceinline__ bool chunk_ref(const WState &w, int64_t g, ChunkRef &
 // an entry's row in the chunk one more, in shared memory; the rows of the chunk a column does not store are implicit
 // zeros and enter min / max and the side histograms by COUNT -- 12 bytes per stored entry visited instead of one
 // search per (row, candidate))
+// ... membership of a stored entry's row in the chunk: one lookup in the inverse map (validated against the index
+// segment: the map is only current for rows of wide nodes) instead of a search among the chunk's rows -- a node deep
+// in the tree is scattered over the whole table, so nearly every stored entry of a candidate column is tested and
+// nearly none is a member; the search was the instruction-bound part of the whole sparse build.
+__device__ __forceinline__ int chunk_pos_inv(const int32_t *inv_tree, const int32_t *idx_tree, int32_t c0, int cnt, int32_t row) {
+  const int32_t at = __ldg(inv_tree + row);
+  const uint32_t pos = (uint32_t)(at - c0);
+  return (pos < (uint32_t)cnt && idx_tree[at] == row) ? (int)pos : -1;
+}
 __device__ __forceinline__ int chunk_pos(const int32_t *s_rows, int cnt, int32_t r) {
   int lo = 0, hi = cnt;
   while (lo < hi) {
@@ -230,6 +242,16 @@ __global__ void __launch_bounds__(1024) k_wide_plan(P p, WState w) {
     __syncthreads();
   }
   if (tid == 0) w.chunk0[w.count] = s_carry;
+}
+
+// sparse-resident tables: the inverse of the index segment for the rows of the wide nodes (one CTA per chunk)
+__global__ void __launch_bounds__(WT) k_wide_inv(P p, WState w) {
+  ChunkRef r;
+  if (!chunk_ref(w, blockIdx.x, r)) return;
+  const WNode &nd = w.node[r.q];
+  const int64_t base = (int64_t)nd.tree * p.n;
+  const int32_t c0 = nd.b + r.j0;
+  for (int32_t j = threadIdx.x; j < r.cnt; j += WT) w.inv[base + p.idx_src[base + c0 + j]] = c0 + j;
 }
 
 // ---- regression: node mean and moments from chunked partial sums --------------------------------------------
@@ -524,6 +546,8 @@ __global__ void __launch_bounds__(WT) k_wide_pass1(P p, WState w) {
     if (p.csc_row) {
       // sparse table: one warp per candidate walks the column's entries inside the chunk's row range
       const int32_t rmin = s_rows[0], rmax = s_rows[r.cnt - 1];
+      const int32_t *inv_tree = w.inv + (int64_t)nd.tree * p.n, *idx_tree = p.idx_src + (int64_t)nd.tree * p.n;
+      const int32_t c0 = nd.b + r.j0;
       for (int c = wit; c < nb; c += WT / 32) {
         const int32_t f = cd.feat[c];
         if (f < 0) continue;
@@ -536,13 +560,13 @@ __global__ void __launch_bounds__(WT) k_wide_pass1(P p, WState w) {
           const bool two = t + 32 < hi;
           const int32_t ra = __ldg(p.csc_row + t), rb = two ? __ldg(p.csc_row + t + 32) : -1;
           const double va = __ldg(p.csc_val + t), vb = two ? __ldg(p.csc_val + t + 32) : 0.0;
-          if (chunk_pos(s_rows, r.cnt, ra) >= 0) {
+          if (chunk_pos_inv(inv_tree, idx_tree, c0, r.cnt, ra) >= 0) {
             members++;
             if (va < mn) mn = va;
             if (va > mx) mx = va;
             nan |= (va != va);
           }
-          if (two && chunk_pos(s_rows, r.cnt, rb) >= 0) {
+          if (two && chunk_pos_inv(inv_tree, idx_tree, c0, r.cnt, rb) >= 0) {
             members++;
             if (vb < mn) mn = vb;
             if (vb > mx) mx = vb;
@@ -856,6 +880,8 @@ __global__ void __launch_bounds__(WT) k_wide_pass2(P p, WState w) {
     }
     __syncthreads();
     const int32_t rmin = s_rows[0], rmax = s_rows[r.cnt - 1];
+    const int32_t *inv_tree = w.inv + (int64_t)nd.tree * p.n, *idx_tree = p.idx_src + (int64_t)nd.tree * p.n;
+    const int32_t c0 = nd.b + r.j0;
     int32_t *gh = w.hist + (int64_t)r.q * 64 * C;
     for (int c = wit; c < nb; c += WT / 32) {
       if (!((act >> c) & 1u)) continue;
@@ -872,7 +898,7 @@ __global__ void __launch_bounds__(WT) k_wide_pass2(P p, WState w) {
         const double v2[2] = {__ldg(p.csc_val + t), two ? __ldg(p.csc_val + t + 32) : 0.0};
 #pragma unroll
         for (int u2 = 0; u2 < 2; u2++) {
-          const int pos = (u2 == 0 || two) ? chunk_pos(s_rows, r.cnt, r2[u2]) : -1;
+          const int pos = (u2 == 0 || two) ? chunk_pos_inv(inv_tree, idx_tree, c0, r.cnt, r2[u2]) : -1;
           if (pos >= 0) {
             const double v = v2[u2];
             const int cls = (int)s_lab8[pos];
@@ -1297,10 +1323,12 @@ __global__ void __launch_bounds__(WT) k_wide_count(P p, WState w) {
       s_w[t] = zero_left ? (rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u)) : 0u;
     }
     __syncthreads();
+    const int32_t *inv_tree = w.inv + (int64_t)nd.tree * p.n, *idx_tree = p.idx_src + (int64_t)nd.tree * p.n;
+    const int32_t c0 = nd.b + r.j0;
     int64_t lo, hi;
     col_range(p, bf, s_rows[0], s_rows[r.cnt - 1], lo, hi);
     for (int64_t t = lo + tid; t < hi; t += WT) {
-      const int pos = chunk_pos(s_rows, r.cnt, __ldg(p.csc_row + t));
+      const int pos = chunk_pos_inv(inv_tree, idx_tree, c0, r.cnt, __ldg(p.csc_row + t));
       if (pos >= 0) {
         const double x = __ldg(p.csc_val + t);
         const bool left = (x < cut) || (mil && (x != x));
@@ -1424,6 +1452,7 @@ struct WideBufs {
   DevBuf<uint32_t> cmask, taken, bits;
   DevBuf<double> part, ysum, park;
   DevBuf<unsigned long long> pending;
+  DevBuf<int32_t> inv;
   bool attr_set = false;
 };
 WideBufs *wide_bufs_create() { return new WideBufs(); }
@@ -1438,7 +1467,11 @@ static int wide_chunk_rows(et_ctx *ctx, int64_t wide_rows, bool sparse_cls) {
   // Sparse-resident table: a chunk walks the stored entries of a column inside its ROW RANGE, and the rows of a node
   // deep in the tree are scattered over the whole table -- a 3000-row node in one chunk tests all 10^4 entries of
   // every candidate column in one CTA.  Small chunks cut the range (and that latency chain) into pieces.
-  if (sparse_cls) return 256;
+  if (sparse_cls) {  // ... as small as keeps the level within a few waves of CTAs (each pays two range searches per candidate)
+    int chunk = 256;
+    while (chunk < 2048 && wide_rows / chunk > (int64_t)ctx->sm_count * 64) chunk <<= 1;
+    return chunk;
+  }
   // enough chunks to fill the GPU a few times over, large enough to amortise the per-chunk staging
   int chunk = WCHUNK_MAX;
   while (chunk > 2048 && wide_rows / chunk < (int64_t)ctx->sm_count * 8) chunk >>= 1;
@@ -1469,6 +1502,7 @@ void wide_level(et_ctx *ctx, const P &p, int32_t count, int64_t wide_rows, const
     wb.ysum.ensure((size_t)max_chunks * 2);
   }
   wb.pending.ensure(2);
+  if (p.csc_row) wb.inv.ensure((size_t)p.inv_rows, 1.0);
   // parked values of pass 1 (FP64 tables): [chunks][stride candidates][chunk rows]; kept within a third of the free HBM
   int park_stride = 0;
   if (!coded && !p.csc_row) {
@@ -1497,6 +1531,7 @@ void wide_level(et_ctx *ctx, const P &p, int32_t count, int64_t wide_rows, const
   w.pending = wb.pending.p;
   w.park = park_stride > 0 ? wb.park.p : nullptr;
   w.park_stride = park_stride;
+  w.inv = p.csc_row ? wb.inv.p : nullptr;
   w.chunk = chunk;
   w.count = count;
   {
@@ -1518,6 +1553,10 @@ void wide_level(et_ctx *ctx, const P &p, int32_t count, int64_t wide_rows, const
   CUDA_CHECK(cudaMemsetAsync(w.pending, 0, 2 * sizeof(unsigned long long), st));
   k_wide_plan<<<1, 1024, 0, st>>>(p, w);
   ctx->launches++;
+  if (p.csc_row) {
+    k_wide_inv<<<gchunks, WT, 0, st>>>(p, w);
+    ctx->launches++;
+  }
   if (TASK == TASK_REG) {
     k_wide_regsum<<<gchunks, WT, 0, st>>>(p, w);
     k_wide_regmom<<<gchunks, WT, 0, st>>>(p, w);
