@@ -140,29 +140,17 @@ __device__ __forceinline__ bool chunk_ref(const WState &w, int64_t g, ChunkRef &
 }
 
 // ---- CSC tables kept sparse: a chunk walks the stored entries of a column that fall into its row range --------
-// (both the chunk's rows and a column's stored rows ascend, so the range is two binary searches and membership of
-// an entry's row in the chunk one more, in shared memory; the rows of the chunk a column does not store are implicit
-// zeros and enter min / max and the side histograms by COUNT -- 12 bytes per stored entry visited instead of one
-// search per (row, candidate))
-// ... membership of a stored entry's row in the chunk: one lookup in the inverse map (validated against the index
-// segment: the map is only current for rows of wide nodes) instead of a search among the chunk's rows -- a node deep
-// in the tree is scattered over the whole table, so nearly every stored entry of a candidate column is tested and
-// nearly none is a member; the search was the instruction-bound part of the whole sparse build.
+// (both the chunk's rows and a column's stored rows ascend, so the chunk's row range is a range of the column: two
+// warp-cooperative searches; the rows of the chunk a column does not store are implicit zeros and enter min / max
+// and the side histograms by COUNT -- 12 bytes per stored entry visited instead of one search per (row, candidate).)
+// Membership of a stored entry's row in the chunk is one lookup in the inverse index map (validated against the
+// index segment: the map is only current for rows of wide nodes) -- a node deep in the tree is scattered over the
+// whole table, so nearly every stored entry of a candidate column is tested and nearly none is a member; a search
+// among the chunk's rows for each was the instruction-bound part of the whole sparse build.
 __device__ __forceinline__ int chunk_pos_inv(const int32_t *inv_tree, const int32_t *idx_tree, int32_t c0, int cnt, int32_t row) {
   const int32_t at = __ldg(inv_tree + row);
   const uint32_t pos = (uint32_t)(at - c0);
   return (pos < (uint32_t)cnt && idx_tree[at] == row) ? (int)pos : -1;
-}
-__device__ __forceinline__ int chunk_pos(const int32_t *s_rows, int cnt, int32_t r) {
-  int lo = 0, hi = cnt;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (s_rows[mid] < r)
-      lo = mid + 1;
-    else
-      hi = mid;
-  }
-  return (lo < cnt && s_rows[lo] == r) ? lo : -1;
 }
 // first entry of [a, e) whose row is >= key (or > key with `past`): the 32 lanes of a warp probe 32 points of the
 // range at once, so a column of 10^4 stored rows is searched in 3 dependent loads instead of 14.  Converged warps only.
