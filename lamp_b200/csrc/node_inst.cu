@@ -102,8 +102,10 @@ void launch_level<ET_TASK>(et_ctx *ctx, const P &p, const int32_t *qn, int64_t w
   // (a quarter of the chain; same draws and same tree, see k_node's lane_mode).  ETGPU_TEAM_MAX moves the bound
   // (nodes per class and level; 0 = never).
   static const int small_nw = lane_small_nw();
-  // (sparse-resident tables: always -- a node's time there is its chain of dependent searches, whatever the level holds)
-  int team_max = p.csc_row ? 0x7fffffff : 2 * 148;
+  // (sparse-resident tables: always -- a node's time there is its chain of dependent searches, whatever the level
+  // holds; dense FP64 tables: off by default -- no gain was measured there, and the two FP64 bench workloads read
+  // 6 % lower in the one run that had it on)
+  int team_max = p.csc_row ? 0x7fffffff : (lc.coded ? 2 * 148 : 0);
   if (const char *env = getenv("ETGPU_TEAM_MAX")) team_max = std::max(0, atoi(env));
   for (int q = Q_WARP; q >= 0; q--) {
     if (qn[q] <= 0) continue;
